@@ -1,0 +1,207 @@
+// blcd_raster.cuh -- row-oriented LCD rasterizer (host+device inline).
+//
+// Replaces WorldEnv.lcd_render (boxLCD/world_env.py:460-512): every dynamic body is drawn as a filled ellipse
+// (circle fixtures) or filled polygon into a 1-bit canvas of lcd_w x lcd_h, flipped top-bottom, background = 1.
+// The reference delegates the fill to Pillow's C rasterizer; the rules restated here (coordinate pipeline, Bresenham
+// ellipse, scanline polygon with apex extension) are the ones pinned against the reference in oracle/lcd_oracle.c.
+//
+// Formulation: instead of drawing shapes into an image, one call computes the ink mask of ONE canvas row for ONE shape;
+// a frame row is the OR over bodies.  A row is one uint32 (bit x = pixel x), so a frame is lcd_h coalesced 4-byte stores
+// and no atomics are needed.  The body transform is evaluated in fp32 WITHOUT fused multiply-add (Box2D's
+// b2Mul(b2Transform, b2Vec2) on x86-64), the metre->pixel scaling in fp64 with truncation toward zero, as the reference.
+#pragma once
+#include "blcd_scene.h"
+
+namespace blcd {
+
+#ifdef __CUDA_ARCH__
+#define BLCD_FMUL(a, b) __fmul_rn(a, b)
+#define BLCD_FADD(a, b) __fadd_rn(a, b)
+#define BLCD_FSUB(a, b) __fsub_rn(a, b)
+#else
+#define BLCD_FMUL(a, b) ((a) * (b))
+#define BLCD_FADD(a, b) ((a) + (b))
+#define BLCD_FSUB(a, b) ((a) - (b))
+#endif
+
+// (int)(v / WIDTH * width) in fp64 (world_env.py:493-505: numpy float64 arithmetic, then PIL's C cast)
+BLCD_HD int to_px(double v, double world_w, double lcd_w) { return (int)(v / world_w * lcd_w); }
+
+// inclusive span [x0, x1] clipped to [0, w) as a bit mask; ends are swapped if inverted (Draw.c hline)
+BLCD_HD uint32_t span_mask(int x0, int x1, int w) {
+  if (x0 > x1) { int t = x0; x0 = x1; x1 = t; }
+  if (x0 < 0) x0 = 0;
+  if (x1 >= w) x1 = w - 1;
+  if (x0 > x1) return 0u;
+  int n = x1 - x0 + 1;
+  uint32_t m = n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u);
+  return m << x0;
+}
+
+BLCD_HD int round_up_px(float f) { return f >= 0.0f ? (int)floor((double)f + 0.5) : -(int)floor(-(double)f + 0.5); }
+BLCD_HD int round_down_px(float f) { return f >= 0.0f ? (int)ceil((double)f - 0.5) : -(int)ceil(-(double)f - 0.5); }
+
+BLCD_HD long long ell_delta(long long a, long long b, long long x, long long y) {
+  long long d = a * a * y * y + b * b * x * x - a * a * b * b;
+  return d < 0 ? -d : d;
+}
+
+// ink of canvas row y for the filled ellipse inscribed in the integer box (x0, y0, x1, y1): Pillow's ellipseNew walk
+// of the first quadrant in doubled coordinates; the widest X reached at height |Y| gives the span of rows +-Y.
+BLCD_HD uint32_t ellipse_row(int x0, int y0, int x1, int y1, int y, int w) {
+  int a = x1 - x0, b = y1 - y0;
+  if (a < 0 || b < 0 || (a == 0 && b == 0)) return 0u;
+  int sy = 2 * (y - y0) - b;
+  int Y = sy < 0 ? -sy : sy;
+  if (Y > b) return 0u;
+  int cx = a, cy = b % 2;
+  const int ex = a % 2, ey = b;
+  while (cy != Y) {  // cy never decreases; the first arrival at cy == Y carries the largest cx of that row
+    if (cx == ex && cy == ey) return 0u;
+    int nx = cx, ny = cy + 2;
+    long long nd = ell_delta(a, b, nx, ny);
+    if (cx > 1) {
+      long long d1 = ell_delta(a, b, cx - 2, cy + 2);
+      if (nd > d1) { nx = cx - 2; ny = cy + 2; nd = d1; }
+      long long d2 = ell_delta(a, b, cx - 2, cy);
+      if (nd > d2) { nx = cx - 2; ny = cy; }
+    }
+    cx = nx; cy = ny;
+  }
+  return span_mask(x0 + (a - cx) / 2, x0 + (a + cx) / 2, w);
+}
+
+struct PolyPx {
+  int n;
+  int x[BLCD_MAX_VERTS], y[BLCD_MAX_VERTS];
+};
+
+BLCD_HD float edge_x_at(int ex0, int ey0, float dx, int y) { return BLCD_FADD(BLCD_FMUL((float)(y - ey0), dx), (float)ex0); }
+
+// ink of canvas row y for the filled polygon with integer vertices P (Pillow polygon_generic restated per row).
+// rules: BLCD_RASTER_PIL12 (pinned) or BLCD_RASTER_PIL9.
+BLCD_HD uint32_t polygon_row(const PolyPx& P, int y, int w, int h, int rules) {
+  const int n = P.n;
+  if (n <= 0) return 0u;
+  // edge list: (P[i], P[i+1]) for i < n-1, plus the closing edge unless the last vertex repeats the first
+  const int ne = (n > 1 && (P.x[n - 1] != P.x[0] || P.y[n - 1] != P.y[0])) ? n : n - 1;
+  if (ne <= 0) return 0u;
+  int ylo = P.y[0], yhi = P.y[0];
+  for (int i = 0; i < ne; ++i) {
+    int j = i + 1 < n ? i + 1 : 0;
+    int a = P.y[i], b = P.y[j];
+    ylo = a < ylo ? a : ylo; ylo = b < ylo ? b : ylo;
+    yhi = a > yhi ? a : yhi; yhi = b > yhi ? b : yhi;
+  }
+  uint32_t mask = 0u;
+  const int Ymin = ylo > 0 ? ylo : 0, Ymax = yhi < h ? yhi : h;
+  float xx[2 * BLCD_MAX_VERTS];
+  int cnt = 0;
+  const bool in_range = (y >= Ymin && y <= Ymax);
+  for (int i = 0; i < ne; ++i) {
+    int j = i + 1 < n ? i + 1 : 0;
+    int ex0 = P.x[i], ey0 = P.y[i], ex1 = P.x[j], ey1 = P.y[j];
+    if (ey0 == ey1) {
+      if (ey0 == y) mask |= span_mask(ex0, ex1, w);
+      continue;
+    }
+    if (!in_range) continue;
+    int emin = ey0 < ey1 ? ey0 : ey1, emax = ey0 < ey1 ? ey1 : ey0;
+    if (emin <= y && y <= emax) {
+      float dx = (float)(ex1 - ex0) / (float)(ey1 - ey0);
+      float xv = edge_x_at(ex0, ey0, dx, y);
+      // insertion into the sorted list (qsort of <= 16 floats in the original)
+      int reps = (y == emax && y < Ymax) ? 2 : 1;
+      for (int r = 0; r < reps; ++r) {
+        int k = cnt++;
+        while (k > 0 && xx[k - 1] > xv) { xx[k] = xx[k - 1]; --k; }
+        xx[k] = xv;
+      }
+    }
+  }
+  if (!in_range) return mask;
+  if (rules == BLCD_RASTER_PIL9) {
+    for (int k = 1; k < cnt; k += 2) mask |= span_mask(round_up_px(xx[k - 1]), round_down_px(xx[k]), w);
+    return mask;
+  }
+  bool have_pos = false;
+  int pos = 0;
+  for (int k = 1; k < cnt; k += 2) {
+    int xs = round_up_px(xx[k - 1]), xe = round_down_px(xx[k]);
+    if (have_pos) {
+      if (xe < pos) continue;
+      if (xs < pos) xs = pos;
+    }
+    if (xe < xs) continue;
+    mask |= span_mask(xs, xe, w);
+    pos = xe + 1; have_pos = true;
+  }
+  // apex extension: two sloped edges of the same direction meeting in an integer vertex on this row
+  for (int i = 0; i < ne; ++i) {
+    int ij = i + 1 < n ? i + 1 : 0;
+    int cx0 = P.x[i], cy0 = P.y[i], cx1 = P.x[ij], cy1 = P.y[ij];
+    if (cy0 == cy1) continue;
+    float cdx = (float)(cx1 - cx0) / (float)(cy1 - cy0);
+    if (cdx == 0.0f) continue;
+    int cmin = cy0 < cy1 ? cy0 : cy1, cmax = cy0 < cy1 ? cy1 : cy0;
+    if (y != cmin && y != cmax) continue;
+    for (int k = 0; k < i; ++k) {
+      int kj = k + 1 < n ? k + 1 : 0;
+      int ox0 = P.x[k], oy0 = P.y[k], ox1 = P.x[kj], oy1 = P.y[kj];
+      if (oy0 == oy1) continue;
+      float odx = (float)(ox1 - ox0) / (float)(oy1 - oy0);
+      if (odx == 0.0f || (cdx > 0.0f) != (odx > 0.0f)) continue;
+      int omin = oy0 < oy1 ? oy0 : oy1, omax = oy0 < oy1 ? oy1 : oy0;
+      bool top = (y == cmin && y == omin);
+      bool bot = (y == cmax && y == omax && y == Ymax);
+      if (!top && !bot) continue;
+      int vx = (cy0 == y) ? cx0 : cx1;
+      int ovx = (oy0 == y) ? ox0 : ox1;
+      if (vx != ovx) continue;
+      int y2 = (y == Ymax) ? y - 1 : y + 1;
+      float a1 = edge_x_at(cx0, cy0, cdx, y2), a2 = edge_x_at(ox0, oy0, odx, y2);
+      if ((bot && cdx > 0.0f) || (top && cdx < 0.0f)) {
+        int s = round_up_px(BLCD_FADD(a1 > a2 ? a1 : a2, 1.0f));
+        if (s <= vx) mask |= span_mask(s, vx, w);
+      } else {
+        int t = round_up_px(a1 < a2 ? a1 : a2) - 1;
+        if (t >= vx) mask |= span_mask(vx, t, w);
+      }
+    }
+  }
+  return mask;
+}
+
+// integer pixel vertices of a polygon fixture under transform (px, py, s, c)
+BLCD_HD void polygon_px(PolyPx& out, const DShape& sh, float px, float py, float s, float c, double world_w, double lcd_w) {
+  out.n = sh.count;
+  for (int i = 0; i < BLCD_MAX_VERTS; ++i) {
+    if (i < sh.count) {
+      float vx = sh.v[i].x, vy = sh.v[i].y;
+      float wx = BLCD_FADD(BLCD_FSUB(BLCD_FMUL(c, vx), BLCD_FMUL(s, vy)), px);
+      float wy = BLCD_FADD(BLCD_FADD(BLCD_FMUL(s, vx), BLCD_FMUL(c, vy)), py);
+      out.x[i] = to_px((double)wx, world_w, lcd_w);
+      out.y[i] = to_px((double)wy, world_w, lcd_w);
+    }
+  }
+}
+
+// ink mask of canvas row y (y-up canvas coordinate) for one body
+BLCD_HD uint32_t body_row(const DShape& sh, float px, float py, float s, float c, int y, int world_w, int lcd_w, int lcd_h, int rules) {
+  const double ww = (double)world_w, lw = (double)lcd_w;
+  if (sh.type == SH_CIRCLE) {
+    const double r = (double)sh.radius;
+    return ellipse_row(to_px((double)px - r, ww, lw), to_px((double)py - r, ww, lw), to_px((double)px + r, ww, lw),
+                       to_px((double)py + r, ww, lw), y, lcd_w);
+  }
+  PolyPx P;
+  polygon_px(P, sh, px, py, s, c, ww, lw);
+  return polygon_row(P, y, lcd_w, lcd_h, rules);
+}
+
+BLCD_HD uint32_t row_bits_from_ink(uint32_t ink, int lcd_w) {
+  uint32_t full = lcd_w >= 32 ? 0xFFFFFFFFu : ((1u << lcd_w) - 1u);
+  return (~ink) & full;
+}
+
+}  // namespace blcd

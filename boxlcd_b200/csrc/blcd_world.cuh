@@ -1,0 +1,1325 @@
+// blcd_world.cuh -- one simulated world per thread: WorldEnv.step's `b2World.Step` x3 (boxLCD/world_env.py:431-458),
+// reset (world_env.py:197-385), _get_obs (world_env.py:387-429) and lcd_render (world_env.py:460-512) for a batch of
+// independent worlds.
+//
+// Mapping: ONE THREAD PER WORLD.  Sequential impulses is a Gauss-Seidel sweep: every constraint reads the velocities the
+// previous one wrote, and in these scenes all joints share the robot root, so there is no constraint-level parallelism
+// to hand to a warp without changing the results.  Throughput comes from world-level parallelism; what the design has
+// to get right is where the per-world working set lives:
+//   * shared memory, laid out [word][thread] (stride = block size, so a warp touches 32 consecutive banks whatever
+//     row each lane indexes): body velocities / positions / inverse masses and the velocity-constraint records of
+//     joints and contacts -- everything the 180 velocity + <=60 position iterations per sub-step touch;
+//   * HBM, laid out [word][world] (a warp reads one 128-byte line per word): the persistent state -- poses, velocities,
+//     sleep timers, fat AABBs, joint warm-start impulses, the ordered contact list and the manifold slots;
+//   * registers / local memory: everything transient (narrow phase, GJK, TOI bookkeeping, island DFS).
+// The same code compiles for the host (tests/hostsim) so that its logic can be diffed bit-for-bit against the CPU oracle.
+#pragma once
+#include "blcd_collide.cuh"
+#include "blcd_raster.cuh"
+
+namespace blcd {
+
+template <int STRIDE>
+struct Hot {
+  float* p;
+  BLCD_HD float& operator[](int i) const { return p[i * STRIDE]; }
+  BLCD_HD uint32_t& u(int i) const { return reinterpret_cast<uint32_t*>(p)[i * STRIDE]; }
+};
+
+struct Gw {  // view of one world's persistent words in HBM
+  uint32_t* p;
+  int64_t n;
+  BLCD_HD uint32_t& u(int i) const { return p[(int64_t)i * n]; }
+  BLCD_HD float& f(int i) const { return reinterpret_cast<float*>(p)[(int64_t)i * n]; }
+};
+
+// Philox4x32-10, counter = (block, world lo, world hi, 0), key = seed
+struct Philox {
+  uint32_t key0, key1, w0, w1, draws;
+  uint32_t buf[4];
+  uint32_t buf_block;
+  BLCD_HD void init(uint64_t seed, uint64_t world, uint32_t d) {
+    key0 = (uint32_t)seed; key1 = (uint32_t)(seed >> 32);
+    w0 = (uint32_t)world; w1 = (uint32_t)(world >> 32);
+    draws = d; buf_block = 0xFFFFFFFFu;
+    buf[0] = buf[1] = buf[2] = buf[3] = 0u;
+  }
+  BLCD_HD void block(uint32_t blk) {
+    uint32_t c0 = blk, c1 = w0, c2 = w1, c3 = 0u, k0 = key0, k1 = key1;
+    for (int r = 0; r < 10; ++r) {
+      uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+      uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+      uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+      uint32_t n1 = (uint32_t)p1;
+      uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+      uint32_t n3 = (uint32_t)p0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    buf[0] = c0; buf[1] = c1; buf[2] = c2; buf[3] = c3;
+    buf_block = blk;
+  }
+  BLCD_HD uint32_t next() {
+    uint32_t blk = draws >> 2;
+    if (blk != buf_block) block(blk);
+    uint32_t lane = draws & 3u;
+    ++draws;
+    return lane == 0 ? buf[0] : (lane == 1 ? buf[1] : (lane == 2 ? buf[2] : buf[3]));
+  }
+  BLCD_HD double uniform(double lo, double hi) { return lo + (hi - lo) * ((double)next() * (1.0 / 4294967296.0)); }
+};
+
+// joint record in shared memory
+enum { J_RAX = 0, J_RAY, J_RBX, J_RBY, J_EXX, J_EYX, J_EZX, J_EYY, J_EZY, J_EZZ, J_MM, J_IX, J_IY, J_IZ, J_MI, J_MS, J_PK };
+// contact record in shared memory
+enum { C_NX = 0, C_NY, C_FR, C_PK, C_K11, C_K12, C_K22, C_N11, C_N12, C_N22, C_PT };
+enum { P_RAX = 0, P_RAY, P_RBX, P_RBY, P_NM, P_TM, P_BIAS, P_NI, P_TI };
+// manifold slot in HBM
+enum { S_HDR = 0, S_LNX, S_LNY, S_LPX, S_LPY, S_PT };  // point j at S_PT + 5 j: x, y, ni, ti, id
+constexpr uint32_t kSlotFree = 0xFFFFFFFFu;
+
+template <int STRIDE>
+struct Sim {
+  const DScene& sc;
+  Hot<STRIDE> hot;
+  Gw g;
+  // body state (registers / local memory)
+  V2 c[BLCD_MAX_BODIES], c0[BLCD_MAX_BODIES], v[BLCD_MAX_BODIES];
+  float a[BLCD_MAX_BODIES], a0[BLCD_MAX_BODIES], w[BLCD_MAX_BODIES], sleepT[BLCD_MAX_BODIES], alpha0[BLCD_MAX_BODIES];
+  Xf xf[BLCD_MAX_BODIES];
+  Box fat[BLCD_MAX_BODIES];
+  float walpha0[BLCD_MAX_WALLS];
+  uint32_t awake, variant, moved;
+  bool newFixture;
+  float inv_dt0;
+  int32_t ep_t;
+  Philox rng;
+  // contacts
+  uint8_t clist[kMaxPairs];
+  int ncl;
+  int8_t pslot[kMaxPairs];
+  uint32_t slotUsed;
+  uint32_t cnt[BLCD_N_COUNTERS];
+  // islands (rebuilt every sub-step)
+  int8_t islandOf[BLCD_MAX_BODIES];
+  int nIslands, nc, njo;
+
+  BLCD_HD Sim(const DScene& s, float* hot_base, uint32_t* state, int64_t n_worlds, int64_t world) : sc(s) {
+    hot.p = hot_base;
+    g.p = state + world;
+    g.n = n_worlds;
+  }
+
+  // ---- scene helpers ------------------------------------------------------------------------------------------------
+  BLCD_HD int var_of(int b) const { return (int)((variant >> b) & 1u); }
+  BLCD_HD const DShape& bshape(int b) const { return sc.body[b].shape[var_of(b)]; }
+  BLCD_HD const DShape& fshape(int f) const { return f < sc.nw ? sc.wall[f] : bshape(f - sc.nw); }
+  BLCD_HD V2 lc_of(int b) const { return sc.body[b].lc[var_of(b)]; }
+  BLCD_HD int row_of(int f) const { return f < sc.nw ? sc.nb : f - sc.nw; }  // row nb = the static body
+  BLCD_HD bool is_awake(int b) const { return (awake >> b) & 1u; }
+  BLCD_HD void set_awake(int b) {  // b2Body::SetAwake(true)
+    if (!is_awake(b)) { awake |= 1u << b; sleepT[b] = 0.0f; }
+  }
+  BLCD_HD void wake_fixture(int f) { if (f >= sc.nw) set_awake(f - sc.nw); }
+  BLCD_HD Xf fxf(int f) const { return f < sc.nw ? xf_identity() : xf[f - sc.nw]; }
+  BLCD_HD Box ffat(int f) const { return f < sc.nw ? sc.wallFat[f] : fat[f - sc.nw]; }
+  // fixture order inside the contact after b2Contact::Create's type-ordering swap
+  BLCD_HD void pair_ab(int p, int* fA, int* fB) const {
+    int fa = sc.pair[p].fa, fb = sc.pair[p].fb;
+    int ta = fshape(fa).type, tb = fshape(fb).type;
+    bool primary = (ta == tb) || (ta == SH_POLY && tb == SH_CIRCLE) || (ta == SH_EDGE);
+    *fA = primary ? fa : fb;
+    *fB = primary ? fb : fa;
+  }
+
+  // ---- HBM <-> thread -----------------------------------------------------------------------------------------------
+  BLCD_HD void load(uint64_t seed, int64_t global_world) {
+    const int nb = sc.nb;
+    uint32_t flags = g.u(sc.off_misc + 0);
+    awake = flags & kAwakeMask;
+    variant = (flags >> kVariantShift) & 0xFFu;
+    newFixture = (flags & kNewFixtureBit) != 0;
+    inv_dt0 = g.f(sc.off_misc + 1);
+    ep_t = (int32_t)g.u(sc.off_misc + 2);
+    rng.init(seed, (uint64_t)global_world, g.u(sc.off_misc + 3));
+    for (int b = 0; b < BLCD_MAX_BODIES; ++b) {
+      if (b < nb) {
+        int o = kBodyWords * b;
+        c[b] = mk(g.f(o + 0), g.f(o + 1)); a[b] = g.f(o + 2);
+        v[b] = mk(g.f(o + 3), g.f(o + 4)); w[b] = g.f(o + 5);
+        sleepT[b] = g.f(o + 6);
+        fat[b].lo = mk(g.f(o + 7), g.f(o + 8)); fat[b].hi = mk(g.f(o + 9), g.f(o + 10));
+        c0[b] = c[b]; a0[b] = a[b]; alpha0[b] = 0.0f;
+        // m_xf.p is kept alongside the sweep: after CreateBody / SetTransform it is the given position, which
+        // c - q * localCenter reproduces only to an ulp when the local centre is not the origin (the luxo head)
+        xf[b].q = rot_of(a[b]);
+        xf[b].p = mk(g.f(o + 11), g.f(o + 12));
+      }
+    }
+    for (int j = 0; j < sc.nj; ++j) {  // joint warm-start state goes straight into its shared-memory record
+      int o = sc.off_joint + kJointWords * j, h = sc.h_joint + kHotJoint * j;
+      hot[h + J_IX] = g.f(o + 0); hot[h + J_IY] = g.f(o + 1); hot[h + J_IZ] = g.f(o + 2);
+      hot[h + J_MI] = g.f(o + 3); hot[h + J_MS] = g.f(o + 4);
+      hot.u(h + J_PK) = g.u(o + 5) & 3u;  // limit state; solve-order fields are filled per sub-step
+    }
+    ncl = (int)g.u(sc.off_clist);
+    for (int k = 0; k < kMaxPairs; ++k) pslot[k] = -1;
+    for (int k = 0; k < ncl; ++k) clist[k] = (uint8_t)((g.u(sc.off_clist + 1 + (k >> 2)) >> (8 * (k & 3))) & 0xFFu);
+    slotUsed = 0u;
+    for (int s = 0; s < sc.maxm; ++s) {
+      uint32_t hdr = g.u(sc.off_slots + kSlotWords * s + S_HDR);
+      if (hdr != kSlotFree) { slotUsed |= 1u << s; pslot[hdr & 0xFFu] = (int8_t)s; }
+    }
+    for (int k = 0; k < BLCD_N_COUNTERS; ++k) cnt[k] = g.u(sc.off_cnt + k);
+    moved = 0u;
+  }
+
+  BLCD_HD void store() {
+    const int nb = sc.nb;
+    g.u(sc.off_misc + 0) = (awake & kAwakeMask) | (variant << kVariantShift) | (newFixture ? kNewFixtureBit : 0u);
+    g.f(sc.off_misc + 1) = inv_dt0;
+    g.u(sc.off_misc + 2) = (uint32_t)ep_t;
+    g.u(sc.off_misc + 3) = rng.draws;
+    for (int b = 0; b < BLCD_MAX_BODIES; ++b) {
+      if (b < nb) {
+        int o = kBodyWords * b;
+        g.f(o + 0) = c[b].x; g.f(o + 1) = c[b].y; g.f(o + 2) = a[b];
+        g.f(o + 3) = v[b].x; g.f(o + 4) = v[b].y; g.f(o + 5) = w[b];
+        g.f(o + 6) = sleepT[b];
+        g.f(o + 7) = fat[b].lo.x; g.f(o + 8) = fat[b].lo.y; g.f(o + 9) = fat[b].hi.x; g.f(o + 10) = fat[b].hi.y;
+        g.f(o + 11) = xf[b].p.x; g.f(o + 12) = xf[b].p.y;
+      }
+    }
+    for (int j = 0; j < sc.nj; ++j) {
+      int o = sc.off_joint + kJointWords * j, h = sc.h_joint + kHotJoint * j;
+      g.f(o + 0) = hot[h + J_IX]; g.f(o + 1) = hot[h + J_IY]; g.f(o + 2) = hot[h + J_IZ];
+      g.f(o + 3) = hot[h + J_MI]; g.f(o + 4) = hot[h + J_MS];
+      g.u(o + 5) = hot.u(h + J_PK) & 3u;
+    }
+    g.u(sc.off_clist) = (uint32_t)ncl;
+    for (int k4 = 0; k4 < sc.clist_words - 1; ++k4) {
+      uint32_t wd = 0u;
+      for (int k = 0; k < 4; ++k) {
+        int i = 4 * k4 + k;
+        if (i < ncl) wd |= (uint32_t)clist[i] << (8 * k);
+      }
+      g.u(sc.off_clist + 1 + k4) = wd;
+    }
+    for (int k = 0; k < BLCD_N_COUNTERS; ++k) g.u(sc.off_cnt + k) = cnt[k];
+  }
+
+  // ---- manifold slots -----------------------------------------------------------------------------------------------
+  BLCD_HD int slot_base(int s) const { return sc.off_slots + kSlotWords * s; }
+  BLCD_HD void slot_write(int s, int p, const Mf& m) {
+    int o = slot_base(s);
+    g.u(o + S_HDR) = (uint32_t)p | ((uint32_t)m.type << 8) | ((uint32_t)m.count << 16);
+    g.f(o + S_LNX) = m.ln.x; g.f(o + S_LNY) = m.ln.y; g.f(o + S_LPX) = m.lp.x; g.f(o + S_LPY) = m.lp.y;
+    for (int j = 0; j < 2; ++j) {
+      if (j < m.count) {
+        int q = o + S_PT + 5 * j;
+        g.f(q + 0) = m.pt[j].x; g.f(q + 1) = m.pt[j].y; g.f(q + 2) = m.ni[j]; g.f(q + 3) = m.ti[j]; g.u(q + 4) = m.id[j];
+      }
+    }
+  }
+
+  // b2Contact::Update for pair p: re-evaluate the manifold at the current transforms, carry warm-start impulses over
+  // by contact id, keep the slot table in step with `touching`.  Returns touching.
+  BLCD_HDN bool update_contact(int p) {
+    int fA, fB;
+    pair_ab(p, &fA, &fB);
+    const DShape &A = fshape(fA), &B = fshape(fB);
+    Mf m;
+    m.count = 0; m.type = 0; m.ln = mk(0.0f, 0.0f); m.lp = mk(0.0f, 0.0f);
+    if (A.type == SH_EDGE) {
+      if (B.type == SH_CIRCLE) collide_edge_circle(m, A, B, fxf(fB));
+      else collide_edge_polygon(m, A, B, fxf(fB));
+    } else if (A.type == SH_CIRCLE) {
+      collide_circles(m, A, fxf(fA), B, fxf(fB));
+    } else if (B.type == SH_CIRCLE) {
+      collide_polygon_circle(m, A, fxf(fA), B, fxf(fB));
+    } else {
+      collide_polygons(m, A, fxf(fA), B, fxf(fB), (sc.flags & BLCD_FLAG_REFFACE_2_3_0) != 0);
+    }
+    int s = pslot[p];
+    bool wasTouching = s >= 0;
+    for (int i = 0; i < 2; ++i) {
+      if (i < m.count) {
+        m.ni[i] = 0.0f; m.ti[i] = 0.0f;
+        if (wasTouching) {
+          int o = slot_base(s);
+          int oldCount = (int)((g.u(o + S_HDR) >> 16) & 0xFFu);
+          for (int j = 0; j < oldCount; ++j) {
+            int q = o + S_PT + 5 * j;
+            if (g.u(q + 4) == m.id[i]) { m.ni[i] = g.f(q + 2); m.ti[i] = g.f(q + 3); break; }
+          }
+        }
+      }
+    }
+    bool touching = m.count > 0;
+    if (touching && s < 0) {  // allocate
+      uint32_t freeMask = ~slotUsed & ((sc.maxm >= 32) ? 0xFFFFFFFFu : ((1u << sc.maxm) - 1u));
+      if (freeMask == 0u) { ++cnt[BLCD_CNT_OVERFLOW]; touching = false; }
+      else {
+        s = 0;
+        while (!((freeMask >> s) & 1u)) ++s;
+        slotUsed |= 1u << s;
+        pslot[p] = (int8_t)s;
+      }
+    }
+    if (touching) slot_write(s, p, m);
+    else if (s >= 0) {  // release
+      g.u(slot_base(s) + S_HDR) = kSlotFree;
+      slotUsed &= ~(1u << s);
+      pslot[p] = -1;
+    }
+    if (touching != wasTouching) { wake_fixture(fA); wake_fixture(fB); }
+    return touching;
+  }
+
+  // ---- broad phase bookkeeping ---------------------------------------------------------------------------------------
+  // b2BroadPhase::UpdatePairs + b2ContactManager::AddPair: candidate pairs are stored in ascending proxy order and each
+  // new contact is pushed to the head of the list, as Box2D does after sorting its pair buffer.
+  BLCD_HDN void find_new_contacts(uint32_t movedMask) {
+    if (movedMask == 0u) return;
+    uint64_t exists = 0ull;
+    for (int k = 0; k < ncl; ++k) exists |= 1ull << clist[k];
+    for (int p = 0; p < sc.np; ++p) {
+      int fa = sc.pair[p].fa, fb = sc.pair[p].fb;
+      if (!(((movedMask >> fa) | (movedMask >> fb)) & 1u)) continue;
+      if ((exists >> p) & 1ull) continue;
+      if (!box_overlap(ffat(fa), ffat(fb))) continue;
+      for (int k = ncl; k > 0; --k) clist[k] = clist[k - 1];
+      clist[0] = (uint8_t)p;
+      ++ncl;
+      wake_fixture(fa);
+      wake_fixture(fb);
+    }
+  }
+
+  // b2Fixture::Synchronize + b2DynamicTree::MoveProxy for body b moving from xf1 to its current transform
+  BLCD_HD void sync_fixture(int b, const Xf& xf1) {
+    const DShape& s = bshape(b);
+    Box b1 = shape_aabb(s, xf1), b2 = shape_aabb(s, xf[b]), bb;
+    bb.lo = mk(fminb(b1.lo.x, b2.lo.x), fminb(b1.lo.y, b2.lo.y));
+    bb.hi = mk(fmaxb(b1.hi.x, b2.hi.x), fmaxb(b1.hi.y, b2.hi.y));
+    if (box_contains(fat[b], bb)) return;
+    V2 disp = xf[b].p - xf1.p;
+    V2 r = mk(kAabbExtension, kAabbExtension);
+    Box f;
+    f.lo = bb.lo - r;
+    f.hi = bb.hi + r;
+    V2 d = kAabbMultiplier * disp;
+    if (d.x < 0.0f) f.lo.x += d.x; else f.hi.x += d.x;
+    if (d.y < 0.0f) f.lo.y += d.y; else f.hi.y += d.y;
+    fat[b] = f;
+    moved |= 1u << (sc.nw + b);
+  }
+
+  // b2ContactManager::Collide
+  BLCD_HDN void collide() {
+    int k = 0;
+    while (k < ncl) {
+      int p = clist[k];
+      int fa = sc.pair[p].fa, fb = sc.pair[p].fb;
+      bool activeA = fa >= sc.nw && is_awake(fa - sc.nw);
+      bool activeB = fb >= sc.nw && is_awake(fb - sc.nw);
+      if (!activeA && !activeB) { ++k; continue; }
+      if (!box_overlap(ffat(fa), ffat(fb))) {  // b2ContactManager::Destroy
+        int s = pslot[p];
+        if (s >= 0) {
+          wake_fixture(fa); wake_fixture(fb);
+          g.u(slot_base(s) + S_HDR) = kSlotFree;
+          slotUsed &= ~(1u << s);
+          pslot[p] = -1;
+        }
+        for (int i = k; i + 1 < ncl; ++i) clist[i] = clist[i + 1];
+        --ncl;
+        continue;
+      }
+      update_contact(p);
+      ++k;
+    }
+  }
+
+  // ---- solver: shared-memory rows ------------------------------------------------------------------------------------
+  BLCD_HD V2 hv(int r) const { return mk(hot[sc.h_vel + 3 * r], hot[sc.h_vel + 3 * r + 1]); }
+  BLCD_HD float hw(int r) const { return hot[sc.h_vel + 3 * r + 2]; }
+  BLCD_HD void set_hv(int r, V2 x, float ww) const { hot[sc.h_vel + 3 * r] = x.x; hot[sc.h_vel + 3 * r + 1] = x.y; hot[sc.h_vel + 3 * r + 2] = ww; }
+  BLCD_HD V2 hc(int r) const { return mk(hot[sc.h_pos + 3 * r], hot[sc.h_pos + 3 * r + 1]); }
+  BLCD_HD float ha(int r) const { return hot[sc.h_pos + 3 * r + 2]; }
+  BLCD_HD void set_hc(int r, V2 x, float aa) const { hot[sc.h_pos + 3 * r] = x.x; hot[sc.h_pos + 3 * r + 1] = x.y; hot[sc.h_pos + 3 * r + 2] = aa; }
+  BLCD_HD float hm(int r) const { return hot[sc.h_mass + 2 * r]; }
+  BLCD_HD float hi(int r) const { return hot[sc.h_mass + 2 * r + 1]; }
+  BLCD_HD V2 row_lc(int r) const { return r < sc.nb ? lc_of(r) : mk(0.0f, 0.0f); }
+
+  BLCD_HD void stage_rows() {
+    for (int b = 0; b < sc.nb; ++b) {
+      set_hv(b, v[b], w[b]);
+      set_hc(b, c[b], a[b]);
+      hot[sc.h_mass + 2 * b] = sc.body[b].invMass[var_of(b)];
+      hot[sc.h_mass + 2 * b + 1] = sc.body[b].invI[var_of(b)];
+    }
+    set_hv(sc.nb, mk(0.0f, 0.0f), 0.0f);
+    set_hc(sc.nb, mk(0.0f, 0.0f), 0.0f);
+    hot[sc.h_mass + 2 * sc.nb] = 0.0f;
+    hot[sc.h_mass + 2 * sc.nb + 1] = 0.0f;
+  }
+
+  // b2ContactSolver ctor + InitializeVelocityConstraints for the manifold in slot s -> contact record k
+  BLCD_HDN void contact_init(int k, int s, int isl, float dtRatio, bool warm) {
+    const int o = slot_base(s), h = sc.h_con + kHotCon * k;
+    uint32_t hdr = g.u(o + S_HDR);
+    int p = (int)(hdr & 0xFFu), type = (int)((hdr >> 8) & 0xFFu), count = (int)((hdr >> 16) & 0xFFu);
+    int fA, fB;
+    pair_ab(p, &fA, &fB);
+    int rA_ = row_of(fA), rB_ = row_of(fB);
+    float radiusA = fshape(fA).radius, radiusB = fshape(fB).radius;
+    float frA = fA < sc.nw ? 0.2f : sc.body[fA - sc.nw].friction, frB = fB < sc.nw ? 0.2f : sc.body[fB - sc.nw].friction;
+    float reA = fA < sc.nw ? 0.0f : sc.body[fA - sc.nw].restitution, reB = fB < sc.nw ? 0.0f : sc.body[fB - sc.nw].restitution;
+    float friction = sqrtf(frA * frB), restitution = reA > reB ? reA : reB;
+    float mA = hm(rA_), iA = hi(rA_), mB = hm(rB_), iB = hi(rB_);
+    V2 cA = hc(rA_), cB = hc(rB_);
+    float aA = ha(rA_), aB = ha(rB_);
+    V2 vA = hv(rA_), vB = hv(rB_);
+    float wA = hw(rA_), wB = hw(rB_);
+    Xf xfA, xfB;
+    xfA.q = rA_ < sc.nb ? rot_of(aA) : rot_identity();
+    xfB.q = rB_ < sc.nb ? rot_of(aB) : rot_identity();
+    xfA.p = cA - rmul(xfA.q, row_lc(rA_));
+    xfB.p = cB - rmul(xfB.q, row_lc(rB_));
+    V2 ln = mk(g.f(o + S_LNX), g.f(o + S_LNY)), lp = mk(g.f(o + S_LPX), g.f(o + S_LPY));
+    V2 normal = mk(1.0f, 0.0f);
+    V2 wp[2];
+    wp[0] = wp[1] = mk(0.0f, 0.0f);
+    // b2WorldManifold::Initialize
+    if (type == MF_CIRCLES) {
+      V2 pointA = xmul(xfA, lp);
+      V2 pointB = xmul(xfB, mk(g.f(o + S_PT), g.f(o + S_PT + 1)));
+      if (dist2(pointA, pointB) > kEps * kEps) { normal = pointB - pointA; normalize(normal); }
+      V2 ca = pointA + radiusA * normal;
+      V2 cb = pointB - radiusB * normal;
+      wp[0] = 0.5f * (ca + cb);
+    } else if (type == MF_FACE_A) {
+      normal = rmul(xfA.q, ln);
+      V2 planePoint = xmul(xfA, lp);
+      for (int j = 0; j < 2; ++j) {
+        if (j < count) {
+          V2 clip = xmul(xfB, mk(g.f(o + S_PT + 5 * j), g.f(o + S_PT + 5 * j + 1)));
+          V2 ca = clip + (radiusA - dot(clip - planePoint, normal)) * normal;
+          V2 cb = clip - radiusB * normal;
+          wp[j] = 0.5f * (ca + cb);
+        }
+      }
+    } else {
+      normal = rmul(xfB.q, ln);
+      V2 planePoint = xmul(xfB, lp);
+      for (int j = 0; j < 2; ++j) {
+        if (j < count) {
+          V2 clip = xmul(xfA, mk(g.f(o + S_PT + 5 * j), g.f(o + S_PT + 5 * j + 1)));
+          V2 cb = clip + (radiusB - dot(clip - planePoint, normal)) * normal;
+          V2 ca = clip - radiusA * normal;
+          wp[j] = 0.5f * (ca + cb);
+        }
+      }
+      normal = -normal;
+    }
+    hot[h + C_NX] = normal.x; hot[h + C_NY] = normal.y; hot[h + C_FR] = friction;
+    V2 tangent = cross(normal, 1.0f);
+    V2 prA[2], prB[2];
+    for (int j = 0; j < 2; ++j) {
+      if (j < count) {
+        int q = h + C_PT + kHotConPt * j;
+        V2 rA = wp[j] - cA, rB = wp[j] - cB;
+        prA[j] = rA; prB[j] = rB;
+        hot[q + P_RAX] = rA.x; hot[q + P_RAY] = rA.y; hot[q + P_RBX] = rB.x; hot[q + P_RBY] = rB.y;
+        float rnA = cross(rA, normal), rnB = cross(rB, normal);
+        float kNormal = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+        hot[q + P_NM] = kNormal > 0.0f ? 1.0f / kNormal : 0.0f;
+        float rtA = cross(rA, tangent), rtB = cross(rB, tangent);
+        float kTangent = mA + mB + iA * rtA * rtA + iB * rtB * rtB;
+        hot[q + P_TM] = kTangent > 0.0f ? 1.0f / kTangent : 0.0f;
+        float bias = 0.0f;
+        float vRel = dot(normal, vB + cross(wB, rB) - vA - cross(wA, rA));
+        if (vRel < -kVelocityThreshold) bias = -restitution * vRel;
+        hot[q + P_BIAS] = bias;
+        hot[q + P_NI] = warm ? dtRatio * g.f(o + S_PT + 5 * j + 2) : 0.0f;
+        hot[q + P_TI] = warm ? dtRatio * g.f(o + S_PT + 5 * j + 3) : 0.0f;
+      }
+    }
+    int pointCount = count;
+    if (count == 2) {
+      float rn1A = cross(prA[0], normal), rn1B = cross(prB[0], normal);
+      float rn2A = cross(prA[1], normal), rn2B = cross(prB[1], normal);
+      float k11 = mA + mB + iA * rn1A * rn1A + iB * rn1B * rn1B;
+      float k22 = mA + mB + iA * rn2A * rn2A + iB * rn2B * rn2B;
+      float k12 = mA + mB + iA * rn1A * rn2A + iB * rn1B * rn2B;
+      if (k11 * k11 < 1000.0f * (k11 * k22 - k12 * k12)) {
+        hot[h + C_K11] = k11; hot[h + C_K12] = k12; hot[h + C_K22] = k22;
+        float det = k11 * k22 - k12 * k12;
+        if (det != 0.0f) det = 1.0f / det;
+        hot[h + C_N11] = det * k22; hot[h + C_N12] = -det * k12; hot[h + C_N22] = det * k11;
+      } else {
+        pointCount = 1;
+      }
+    }
+    hot.u(h + C_PK) = (uint32_t)rA_ | ((uint32_t)rB_ << 4) | ((uint32_t)pointCount << 8) | ((uint32_t)s << 12) | ((uint32_t)isl << 20);
+  }
+
+  BLCD_HD void contact_warm_start(int k) {
+    const int h = sc.h_con + kHotCon * k;
+    uint32_t pk = hot.u(h + C_PK);
+    int rA_ = pk & 15u, rB_ = (pk >> 4) & 15u, count = (pk >> 8) & 15u;
+    float mA = hm(rA_), iA = hi(rA_), mB = hm(rB_), iB = hi(rB_);
+    V2 vA = hv(rA_), vB = hv(rB_);
+    float wA = hw(rA_), wB = hw(rB_);
+    V2 normal = mk(hot[h + C_NX], hot[h + C_NY]);
+    V2 tangent = cross(normal, 1.0f);
+    for (int j = 0; j < 2; ++j) {
+      if (j < count) {
+        int q = h + C_PT + kHotConPt * j;
+        V2 rA = mk(hot[q + P_RAX], hot[q + P_RAY]), rB = mk(hot[q + P_RBX], hot[q + P_RBY]);
+        V2 P = hot[q + P_NI] * normal + hot[q + P_TI] * tangent;
+        wA -= iA * cross(rA, P);
+        vA -= mA * P;
+        wB += iB * cross(rB, P);
+        vB += mB * P;
+      }
+    }
+    set_hv(rA_, vA, wA);
+    set_hv(rB_, vB, wB);
+  }
+
+  BLCD_HD void contact_solve_velocity(int k) {
+    const int h = sc.h_con + kHotCon * k;
+    uint32_t pk = hot.u(h + C_PK);
+    int rA_ = pk & 15u, rB_ = (pk >> 4) & 15u, count = (pk >> 8) & 15u;
+    float mA = hm(rA_), iA = hi(rA_), mB = hm(rB_), iB = hi(rB_);
+    V2 vA = hv(rA_), vB = hv(rB_);
+    float wA = hw(rA_), wB = hw(rB_);
+    V2 normal = mk(hot[h + C_NX], hot[h + C_NY]);
+    V2 tangent = cross(normal, 1.0f);
+    float friction = hot[h + C_FR];
+    for (int j = 0; j < 2; ++j) {
+      if (j < count) {
+        int q = h + C_PT + kHotConPt * j;
+        V2 rA = mk(hot[q + P_RAX], hot[q + P_RAY]), rB = mk(hot[q + P_RBX], hot[q + P_RBY]);
+        V2 dv = vB + cross(wB, rB) - vA - cross(wA, rA);
+        float vt = dot(dv, tangent) - 0.0f;
+        float lambda = hot[q + P_TM] * (-vt);
+        float maxFriction = friction * hot[q + P_NI];
+        float oldImpulse = hot[q + P_TI];
+        float newImpulse = clampb(oldImpulse + lambda, -maxFriction, maxFriction);
+        lambda = newImpulse - oldImpulse;
+        hot[q + P_TI] = newImpulse;
+        V2 P = lambda * tangent;
+        vA -= mA * P;
+        wA -= iA * cross(rA, P);
+        vB += mB * P;
+        wB += iB * cross(rB, P);
+      }
+    }
+    if (count == 1) {
+      int q = h + C_PT;
+      V2 rA = mk(hot[q + P_RAX], hot[q + P_RAY]), rB = mk(hot[q + P_RBX], hot[q + P_RBY]);
+      V2 dv = vB + cross(wB, rB) - vA - cross(wA, rA);
+      float vn = dot(dv, normal);
+      float lambda = -hot[q + P_NM] * (vn - hot[q + P_BIAS]);
+      float oldImpulse = hot[q + P_NI];
+      float newImpulse = fmaxb(oldImpulse + lambda, 0.0f);
+      lambda = newImpulse - oldImpulse;
+      hot[q + P_NI] = newImpulse;
+      V2 P = lambda * normal;
+      vA -= mA * P;
+      wA -= iA * cross(rA, P);
+      vB += mB * P;
+      wB += iB * cross(rB, P);
+    } else if (count == 2) {
+      int q1 = h + C_PT, q2 = h + C_PT + kHotConPt;
+      V2 r1A = mk(hot[q1 + P_RAX], hot[q1 + P_RAY]), r1B = mk(hot[q1 + P_RBX], hot[q1 + P_RBY]);
+      V2 r2A = mk(hot[q2 + P_RAX], hot[q2 + P_RAY]), r2B = mk(hot[q2 + P_RBX], hot[q2 + P_RBY]);
+      V2 aa = mk(hot[q1 + P_NI], hot[q2 + P_NI]);
+      V2 dv1 = vB + cross(wB, r1B) - vA - cross(wA, r1A);
+      V2 dv2 = vB + cross(wB, r2B) - vA - cross(wA, r2A);
+      float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
+      V2 b = mk(vn1 - hot[q1 + P_BIAS], vn2 - hot[q2 + P_BIAS]);
+      float k11 = hot[h + C_K11], k12 = hot[h + C_K12], k22 = hot[h + C_K22];
+      b -= mk(k11 * aa.x + k12 * aa.y, k12 * aa.x + k22 * aa.y);
+      V2 x;
+      bool found = true;
+      {
+        float n11 = hot[h + C_N11], n12 = hot[h + C_N12], n22 = hot[h + C_N22];
+        x = -mk(n11 * b.x + n12 * b.y, n12 * b.x + n22 * b.y);
+        if (!(x.x >= 0.0f && x.y >= 0.0f)) {
+          x.x = -hot[q1 + P_NM] * b.x; x.y = 0.0f;
+          vn2 = k12 * x.x + b.y;
+          if (!(x.x >= 0.0f && vn2 >= 0.0f)) {
+            x.x = 0.0f; x.y = -hot[q2 + P_NM] * b.y;
+            vn1 = k12 * x.y + b.x;
+            if (!(x.y >= 0.0f && vn1 >= 0.0f)) {
+              x.x = 0.0f; x.y = 0.0f;
+              found = (b.x >= 0.0f && b.y >= 0.0f);
+            }
+          }
+        }
+      }
+      if (found) {
+        V2 d = x - aa;
+        V2 P1 = d.x * normal, P2 = d.y * normal;
+        vA -= mA * (P1 + P2);
+        wA -= iA * (cross(r1A, P1) + cross(r2A, P2));
+        vB += mB * (P1 + P2);
+        wB += iB * (cross(r1B, P1) + cross(r2B, P2));
+        hot[q1 + P_NI] = x.x;
+        hot[q2 + P_NI] = x.y;
+      }
+    }
+    set_hv(rA_, vA, wA);
+    set_hv(rB_, vB, wB);
+  }
+
+  BLCD_HD void contact_store_impulses(int k) {
+    const int h = sc.h_con + kHotCon * k;
+    uint32_t pk = hot.u(h + C_PK);
+    int count = (pk >> 8) & 15u, s = (pk >> 12) & 255u;
+    int o = slot_base(s);
+    for (int j = 0; j < 2; ++j) {
+      if (j < count) {
+        int q = h + C_PT + kHotConPt * j;
+        g.f(o + S_PT + 5 * j + 2) = hot[q + P_NI];
+        g.f(o + S_PT + 5 * j + 3) = hot[q + P_TI];
+      }
+    }
+  }
+
+  // one pass of b2ContactSolver::SolvePositionConstraints / SolveTOIPositionConstraints over contact record k;
+  // returns the smallest separation seen
+  BLCD_HD float contact_solve_position(int k, float baumgarte) {
+    const int h = sc.h_con + kHotCon * k;
+    uint32_t pk = hot.u(h + C_PK);
+    int rA_ = pk & 15u, rB_ = (pk >> 4) & 15u, s = (pk >> 12) & 255u;
+    const int o = slot_base(s);
+    uint32_t hdr = g.u(o + S_HDR);
+    int p = (int)(hdr & 0xFFu), type = (int)((hdr >> 8) & 0xFFu), count = (int)((hdr >> 16) & 0xFFu);
+    int fA, fB;
+    pair_ab(p, &fA, &fB);
+    float radiusA = fshape(fA).radius, radiusB = fshape(fB).radius;
+    V2 lcA = row_lc(rA_), lcB = row_lc(rB_);
+    float mA = hm(rA_), iA = hi(rA_), mB = hm(rB_), iB = hi(rB_);
+    V2 cA = hc(rA_), cB = hc(rB_);
+    float aA = ha(rA_), aB = ha(rB_);
+    V2 ln = mk(g.f(o + S_LNX), g.f(o + S_LNY)), lp = mk(g.f(o + S_LPX), g.f(o + S_LPY));
+    float minSeparation = 0.0f;
+    for (int j = 0; j < 2; ++j) {
+      if (j < count) {
+        Xf xfA, xfB;
+        xfA.q = rA_ < sc.nb ? rot_of(aA) : rot_identity();
+        xfB.q = rB_ < sc.nb ? rot_of(aB) : rot_identity();
+        xfA.p = cA - rmul(xfA.q, lcA);
+        xfB.p = cB - rmul(xfB.q, lcB);
+        V2 lpt = mk(g.f(o + S_PT + 5 * j), g.f(o + S_PT + 5 * j + 1));
+        V2 normal, point;
+        float separation;
+        if (type == MF_CIRCLES) {
+          V2 pointA = xmul(xfA, lp);
+          V2 pointB = xmul(xfB, mk(g.f(o + S_PT), g.f(o + S_PT + 1)));
+          normal = pointB - pointA;
+          normalize(normal);
+          point = 0.5f * (pointA + pointB);
+          separation = dot(pointB - pointA, normal) - radiusA - radiusB;
+        } else if (type == MF_FACE_A) {
+          normal = rmul(xfA.q, ln);
+          V2 planePoint = xmul(xfA, lp);
+          V2 clip = xmul(xfB, lpt);
+          separation = dot(clip - planePoint, normal) - radiusA - radiusB;
+          point = clip;
+        } else {
+          normal = rmul(xfB.q, ln);
+          V2 planePoint = xmul(xfB, lp);
+          V2 clip = xmul(xfA, lpt);
+          separation = dot(clip - planePoint, normal) - radiusA - radiusB;
+          point = clip;
+          normal = -normal;
+        }
+        V2 rA = point - cA, rB = point - cB;
+        minSeparation = fminb(minSeparation, separation);
+        float C = clampb(baumgarte * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
+        float rnA = cross(rA, normal), rnB = cross(rB, normal);
+        float K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+        float impulse = K > 0.0f ? -C / K : 0.0f;
+        V2 P = impulse * normal;
+        cA -= mA * P;
+        aA -= iA * cross(rA, P);
+        cB += mB * P;
+        aB += iB * cross(rB, P);
+      }
+    }
+    set_hc(rA_, cA, aA);
+    set_hc(rB_, cB, aB);
+    return minSeparation;
+  }
+
+  // ---- revolute joints (b2RevoluteJoint) -----------------------------------------------------------------------------
+  // record k (solve order) is built for joint id j; warm-start impulses were staged at record position j by load()
+  // and are kept at their joint-id position: record index == joint id, solve order is a separate small table.
+  BLCD_HDN void joint_init(int j, int isl, float dtRatio, float h_dt) {
+    const DJoint& jd = sc.joint[j];
+    const int h = sc.h_joint + kHotJoint * j;
+    int rA_ = jd.a, rB_ = jd.b;
+    float mA = hm(rA_), iA = hi(rA_), mB = hm(rB_), iB = hi(rB_);
+    float aA = ha(rA_), aB = ha(rB_);
+    V2 vA = hv(rA_), vB = hv(rB_);
+    float wA = hw(rA_), wB = hw(rB_);
+    Rot qA = rot_of(aA), qB = rot_of(aB);
+    V2 rA = rmul(qA, jd.la - lc_of(rA_));
+    V2 rB = rmul(qB, jd.lb - lc_of(rB_));
+    bool fixedRotation = (iA + iB == 0.0f);
+    hot[h + J_RAX] = rA.x; hot[h + J_RAY] = rA.y; hot[h + J_RBX] = rB.x; hot[h + J_RBY] = rB.y;
+    hot[h + J_EXX] = mA + mB + rA.y * rA.y * iA + rB.y * rB.y * iB;
+    hot[h + J_EYX] = -rA.y * rA.x * iA - rB.y * rB.x * iB;
+    hot[h + J_EZX] = -rA.y * iA - rB.y * iB;
+    hot[h + J_EYY] = mA + mB + rA.x * rA.x * iA + rB.x * rB.x * iB;
+    hot[h + J_EZY] = rA.x * iA + rB.x * iB;
+    hot[h + J_EZZ] = iA + iB;
+    float motorMass = iA + iB;
+    if (motorMass > 0.0f) motorMass = 1.0f / motorMass;
+    hot[h + J_MM] = motorMass;
+    float impx = hot[h + J_IX], impy = hot[h + J_IY], impz = hot[h + J_IZ], motorImpulse = hot[h + J_MI];
+    int limitState = (int)(hot.u(h + J_PK) & 3u);
+    if (!jd.enableMotor || fixedRotation) motorImpulse = 0.0f;
+    if (jd.enableLimit && !fixedRotation) {
+      float jointAngle = aB - aA - 0.0f;  // referenceAngle = 0 (world_env.py:255-266)
+      if (absb(jd.upper - jd.lower) < 2.0f * kAngularSlop) limitState = 3;
+      else if (jointAngle <= jd.lower) { if (limitState != 1) impz = 0.0f; limitState = 1; }
+      else if (jointAngle >= jd.upper) { if (limitState != 2) impz = 0.0f; limitState = 2; }
+      else { limitState = 0; impz = 0.0f; }
+    } else {
+      limitState = 0;
+    }
+    impx *= dtRatio; impy *= dtRatio; impz *= dtRatio;
+    motorImpulse *= dtRatio;
+    V2 P = mk(impx, impy);
+    vA -= mA * P;
+    wA -= iA * (cross(rA, P) + motorImpulse + impz);
+    vB += mB * P;
+    wB += iB * (cross(rB, P) + motorImpulse + impz);
+    hot[h + J_IX] = impx; hot[h + J_IY] = impy; hot[h + J_IZ] = impz; hot[h + J_MI] = motorImpulse;
+    hot.u(h + J_PK) = (uint32_t)limitState | ((uint32_t)isl << 4) | ((fixedRotation ? 1u : 0u) << 8);
+    (void)h_dt;
+    set_hv(rA_, vA, wA);
+    set_hv(rB_, vB, wB);
+  }
+
+  BLCD_HD void joint_solve_velocity(int j, float h_dt) {
+    const DJoint& jd = sc.joint[j];
+    const int h = sc.h_joint + kHotJoint * j;
+    int rA_ = jd.a, rB_ = jd.b;
+    float mA = hm(rA_), iA = hi(rA_), mB = hm(rB_), iB = hi(rB_);
+    V2 vA = hv(rA_), vB = hv(rB_);
+    float wA = hw(rA_), wB = hw(rB_);
+    uint32_t pk = hot.u(h + J_PK);
+    int limitState = pk & 3u;
+    bool fixedRotation = (pk >> 8) & 1u;
+    V2 rA = mk(hot[h + J_RAX], hot[h + J_RAY]), rB = mk(hot[h + J_RBX], hot[h + J_RBY]);
+    if (jd.enableMotor && limitState != 3 && !fixedRotation) {
+      float Cdot = wB - wA - hot[h + J_MS];
+      float impulse = -hot[h + J_MM] * Cdot;
+      float oldImpulse = hot[h + J_MI];
+      float maxImpulse = h_dt * jd.maxTorque;
+      float ni = clampb(oldImpulse + impulse, -maxImpulse, maxImpulse);
+      hot[h + J_MI] = ni;
+      impulse = ni - oldImpulse;
+      wA -= iA * impulse;
+      wB += iB * impulse;
+    }
+    float exx = hot[h + J_EXX], eyx = hot[h + J_EYX], eyy = hot[h + J_EYY];
+    if (jd.enableLimit && limitState != 0 && !fixedRotation) {
+      float ezx = hot[h + J_EZX], ezy = hot[h + J_EZY], ezz = hot[h + J_EZZ];
+      V2 Cdot1 = vB + cross(wB, rB) - vA - cross(wA, rA);
+      float Cdot2 = wB - wA;
+      // b2Mat33::Solve33 with ex = (exx, eyx, ezx), ey = (eyx, eyy, ezy), ez = (ezx, ezy, ezz)
+      float bx = Cdot1.x, by = Cdot1.y, bz = Cdot2;
+      float cx_ = eyy * ezz - ezy * ezy, cy_ = ezy * ezx - eyx * ezz, cz_ = eyx * ezy - eyy * ezx;  // cross(ey, ez)
+      float det = exx * cx_ + eyx * cy_ + ezx * cz_;
+      if (det != 0.0f) det = 1.0f / det;
+      float ix = det * (bx * cx_ + by * cy_ + bz * cz_);
+      float ux = by * ezz - bz * ezy, uy = bz * ezx - bx * ezz, uz = bx * ezy - by * ezx;        // cross(b, ez)
+      float iy = det * (exx * ux + eyx * uy + ezx * uz);
+      float tx = eyy * bz - ezy * by, ty = ezy * bx - eyx * bz, tz = eyx * by - eyy * bx;        // cross(ey, b)
+      float iz = det * (exx * tx + eyx * ty + ezx * tz);
+      ix = -ix; iy = -iy; iz = -iz;
+      float jx = hot[h + J_IX], jy = hot[h + J_IY], jz = hot[h + J_IZ];
+      bool reduce = false;
+      if (limitState == 1) reduce = (jz + iz) < 0.0f;
+      else if (limitState == 2) reduce = (jz + iz) > 0.0f;
+      if (reduce) {
+        V2 rhs = -Cdot1 + jz * mk(ezx, ezy);
+        float d2 = exx * eyy - eyx * eyx;
+        if (d2 != 0.0f) d2 = 1.0f / d2;
+        float redx = d2 * (eyy * rhs.x - eyx * rhs.y), redy = d2 * (exx * rhs.y - eyx * rhs.x);
+        ix = redx; iy = redy; iz = -jz;
+        jx += redx; jy += redy; jz = 0.0f;
+      } else {
+        jx += ix; jy += iy; jz += iz;
+      }
+      hot[h + J_IX] = jx; hot[h + J_IY] = jy; hot[h + J_IZ] = jz;
+      V2 P = mk(ix, iy);
+      vA -= mA * P;
+      wA -= iA * (cross(rA, P) + iz);
+      vB += mB * P;
+      wB += iB * (cross(rB, P) + iz);
+    } else {
+      V2 Cdot = vB + cross(wB, rB) - vA - cross(wA, rA);
+      V2 nb_ = -Cdot;
+      float d2 = exx * eyy - eyx * eyx;
+      if (d2 != 0.0f) d2 = 1.0f / d2;
+      V2 imp = mk(d2 * (eyy * nb_.x - eyx * nb_.y), d2 * (exx * nb_.y - eyx * nb_.x));
+      hot[h + J_IX] += imp.x;
+      hot[h + J_IY] += imp.y;
+      vA -= mA * imp;
+      wA -= iA * cross(rA, imp);
+      vB += mB * imp;
+      wB += iB * cross(rB, imp);
+    }
+    set_hv(rA_, vA, wA);
+    set_hv(rB_, vB, wB);
+  }
+
+  BLCD_HD bool joint_solve_position(int j) {
+    const DJoint& jd = sc.joint[j];
+    const int h = sc.h_joint + kHotJoint * j;
+    int rA_ = jd.a, rB_ = jd.b;
+    float mA = hm(rA_), iA = hi(rA_), mB = hm(rB_), iB = hi(rB_);
+    V2 cA = hc(rA_), cB = hc(rB_);
+    float aA = ha(rA_), aB = ha(rB_);
+    uint32_t pk = hot.u(h + J_PK);
+    int limitState = pk & 3u;
+    bool fixedRotation = (pk >> 8) & 1u;
+    float angularError = 0.0f, positionError = 0.0f;
+    if (jd.enableLimit && limitState != 0 && !fixedRotation) {
+      float angle = aB - aA - 0.0f;
+      float limitImpulse = 0.0f;
+      float motorMass = hot[h + J_MM];
+      if (limitState == 3) {
+        float C = clampb(angle - jd.lower, -kMaxAngularCorrection, kMaxAngularCorrection);
+        limitImpulse = -motorMass * C;
+        angularError = absb(C);
+      } else if (limitState == 1) {
+        float C = angle - jd.lower;
+        angularError = -C;
+        C = clampb(C + kAngularSlop, -kMaxAngularCorrection, 0.0f);
+        limitImpulse = -motorMass * C;
+      } else {
+        float C = angle - jd.upper;
+        angularError = C;
+        C = clampb(C - kAngularSlop, 0.0f, kMaxAngularCorrection);
+        limitImpulse = -motorMass * C;
+      }
+      aA -= iA * limitImpulse;
+      aB += iB * limitImpulse;
+    }
+    {
+      Rot qA = rot_of(aA), qB = rot_of(aB);
+      V2 rA = rmul(qA, jd.la - lc_of(rA_));
+      V2 rB = rmul(qB, jd.lb - lc_of(rB_));
+      V2 C = cB + rB - cA - rA;
+      positionError = len(C);
+      float kxx = mA + mB + iA * rA.y * rA.y + iB * rB.y * rB.y;
+      float kxy = -iA * rA.x * rA.y - iB * rB.x * rB.y;
+      float kyy = mA + mB + iA * rA.x * rA.x + iB * rB.x * rB.x;
+      float det = kxx * kyy - kxy * kxy;
+      if (det != 0.0f) det = 1.0f / det;
+      V2 imp = -mk(det * (kyy * C.x - kxy * C.y), det * (kxx * C.y - kxy * C.x));
+      cA -= mA * imp;
+      aA -= iA * cross(rA, imp);
+      cB += mB * imp;
+      aB += iB * cross(rB, imp);
+    }
+    set_hc(rA_, cA, aA);
+    set_hc(rB_, cB, aB);
+    return positionError <= kLinearSlop && angularError <= kAngularSlop;
+  }
+
+  // ---- b2World::Solve -------------------------------------------------------------------------------------------------
+  BLCD_HDN void solve(float h_dt, float dtRatio) {
+    const int nb = sc.nb;
+    uint8_t corder[32];           // contact record k -> nothing to map: records are filled in solve order
+    uint8_t jorder[BLCD_MAX_JOINTS];
+    uint8_t jisl[BLCD_MAX_JOINTS];
+    uint8_t stack[BLCD_MAX_BODIES];
+    uint64_t cflag = 0ull;
+    uint32_t jflag = 0u;
+    (void)corder;
+    for (int b = 0; b < BLCD_MAX_BODIES; ++b) islandOf[b] = -1;
+    nIslands = 0; nc = 0; njo = 0;
+    stage_rows();
+    // island DFS in Box2D's order: seeds newest body first; per body its contact edges (newest first) then joint edges
+    for (int seed = nb - 1; seed >= 0; --seed) {
+      if (islandOf[seed] >= 0 || !is_awake(seed)) continue;
+      int isl = nIslands++;
+      int sp = 0;
+      stack[sp++] = (uint8_t)seed;
+      islandOf[seed] = (int8_t)isl;
+      while (sp > 0) {
+        int b = stack[--sp];
+        set_awake(b);
+        int fb_ = sc.nw + b;
+        for (int k = 0; k < ncl; ++k) {
+          int p = clist[k];
+          int fa = sc.pair[p].fa, fb = sc.pair[p].fb;
+          if (fa != fb_ && fb != fb_) continue;
+          if ((cflag >> p) & 1ull) continue;
+          int s = pslot[p];
+          if (s < 0) continue;  // not touching
+          cflag |= 1ull << p;
+          if (nc < sc.maxm) {
+            // record filled later (needs integrated velocities); remember slot + island in the packed word
+            hot.u(sc.h_con + kHotCon * nc + C_PK) = ((uint32_t)s << 12) | ((uint32_t)isl << 20);
+            ++nc;
+          }
+          int other = fa == fb_ ? fb : fa;
+          if (other < sc.nw) continue;  // static bodies are not expanded
+          int ob = other - sc.nw;
+          if (islandOf[ob] >= 0) continue;
+          stack[sp++] = (uint8_t)ob;
+          islandOf[ob] = (int8_t)isl;
+        }
+        const DBody& bd = sc.body[b];
+        for (int e = 0; e < bd.njedge; ++e) {
+          int j = bd.jedge[e];
+          if ((jflag >> j) & 1u) continue;
+          jflag |= 1u << j;
+          jorder[njo] = (uint8_t)j; jisl[njo] = (uint8_t)isl;
+          ++njo;
+          int ob = sc.joint[j].a == b ? sc.joint[j].b : sc.joint[j].a;
+          if (islandOf[ob] >= 0) continue;
+          stack[sp++] = (uint8_t)ob;
+          islandOf[ob] = (int8_t)isl;
+        }
+      }
+    }
+    cnt[BLCD_CNT_CONTACTS] += (uint32_t)nc;
+    // b2Island::Solve: integrate velocities (gravity, damping)
+    for (int b = 0; b < nb; ++b) {
+      if (islandOf[b] < 0) continue;
+      c0[b] = c[b]; a0[b] = a[b];
+      V2 vv = v[b];
+      float ww = w[b];
+      float im = hm(b), ii = hi(b);
+      vv += h_dt * (1.0f * sc.gravity + im * mk(0.0f, 0.0f));
+      ww += h_dt * ii * 0.0f;
+      if (sc.flags & BLCD_FLAG_DAMPING_2_3_0) {
+        vv *= clampb(1.0f - h_dt * sc.body[b].linDamp, 0.0f, 1.0f);
+        ww *= clampb(1.0f - h_dt * sc.body[b].angDamp, 0.0f, 1.0f);
+      } else {
+        vv *= 1.0f / (1.0f + h_dt * sc.body[b].linDamp);
+        ww *= 1.0f / (1.0f + h_dt * sc.body[b].angDamp);
+      }
+      set_hv(b, vv, ww);
+    }
+    for (int k = 0; k < nc; ++k) {
+      uint32_t pk = hot.u(sc.h_con + kHotCon * k + C_PK);
+      contact_init(k, (int)((pk >> 12) & 255u), (int)(pk >> 20), dtRatio, true);
+    }
+    for (int k = 0; k < nc; ++k) contact_warm_start(k);
+    for (int k = 0; k < njo; ++k) joint_init(jorder[k], jisl[k], dtRatio, h_dt);
+    const int vi = sc.vel_iters;
+    for (int it = 0; it < vi; ++it) {
+      for (int k = 0; k < njo; ++k) joint_solve_velocity(jorder[k], h_dt);
+      for (int k = 0; k < nc; ++k) contact_solve_velocity(k);
+    }
+    for (int k = 0; k < nc; ++k) contact_store_impulses(k);
+    // integrate positions
+    for (int b = 0; b < nb; ++b) {
+      if (islandOf[b] < 0) continue;
+      V2 cc = hc(b), vv = hv(b);
+      float aa = ha(b), ww = hw(b);
+      V2 translation = h_dt * vv;
+      if (dot(translation, translation) > kMaxTranslationSq) { float ratio = kMaxTranslation / len(translation); vv *= ratio; }
+      float rotation = h_dt * ww;
+      if (rotation * rotation > kMaxRotationSq) { float ratio = kMaxRotation / absb(rotation); ww *= ratio; }
+      cc += h_dt * vv;
+      aa += h_dt * ww;
+      set_hc(b, cc, aa);
+      set_hv(b, vv, ww);
+    }
+    // position iterations; every island stops on its own convergence
+    uint32_t islDone = 0u;
+    const uint32_t islAll = (1u << nIslands) - 1u;
+    for (int it = 0; it < sc.pos_iters && islDone != islAll; ++it) {
+      uint32_t bad = 0u;
+      cnt[BLCD_CNT_POS_ITERS] += (uint32_t)(nIslands - popc(islDone));
+      for (int k = 0; k < nc; ++k) {
+        int isl = (int)(hot.u(sc.h_con + kHotCon * k + C_PK) >> 20);
+        if ((islDone >> isl) & 1u) continue;
+        float ms = contact_solve_position(k, kBaumgarte);
+        if (!(ms >= -3.0f * kLinearSlop)) bad |= 1u << isl;
+      }
+      for (int k = 0; k < njo; ++k) {
+        int isl = jisl[k];
+        if ((islDone >> isl) & 1u) continue;
+        if (!joint_solve_position(jorder[k])) bad |= 1u << isl;
+      }
+      islDone |= ~bad & islAll;
+    }
+    // write back + SynchronizeTransform
+    Xf xf1[BLCD_MAX_BODIES];
+    for (int b = 0; b < nb; ++b) {
+      if (islandOf[b] < 0) continue;
+      xf1[b] = xf[b];  // transform at (c0, a0)
+      c[b] = hc(b); a[b] = ha(b);
+      v[b] = hv(b); w[b] = hw(b);
+      xf[b] = xf_of(c[b], a[b], lc_of(b));
+    }
+    // sleeping (per island)
+    if (!(sc.flags & BLCD_FLAG_NO_SLEEP)) {
+      for (int isl = 0; isl < nIslands; ++isl) {
+        float minSleep = kMaxFloat;
+        for (int b = 0; b < nb; ++b) {
+          if (islandOf[b] != isl) continue;
+          if (w[b] * w[b] > kAngSleepTol * kAngSleepTol || dot(v[b], v[b]) > kLinSleepTol * kLinSleepTol) {
+            sleepT[b] = 0.0f;
+            minSleep = 0.0f;
+          } else {
+            sleepT[b] += h_dt;
+            minSleep = fminb(minSleep, sleepT[b]);
+          }
+        }
+        if (minSleep >= kTimeToSleep && ((islDone >> isl) & 1u)) {
+          for (int b = 0; b < nb; ++b) {
+            if (islandOf[b] != isl) continue;
+            awake &= ~(1u << b);
+            sleepT[b] = 0.0f;
+            v[b] = mk(0.0f, 0.0f);
+            w[b] = 0.0f;
+          }
+        }
+      }
+    }
+    // broad phase: newest body first, then b2ContactManager::FindNewContacts
+    moved = 0u;
+    for (int b = nb - 1; b >= 0; --b) {
+      if (islandOf[b] < 0) continue;
+      sync_fixture(b, xf1[b]);
+    }
+    find_new_contacts(moved);
+    moved = 0u;
+  }
+
+  BLCD_HD static int popc(uint32_t x) {
+    int n = 0;
+    while (x) { x &= x - 1u; ++n; }
+    return n;
+  }
+
+  // ---- b2World::SolveTOI: continuous collision of awake dynamic bodies against the static walls ----------------------
+  BLCD_HDN void solve_toi(float h_dt) {
+    const int nb = sc.nb, nw = sc.nw;
+    float toi[kMaxPairs];
+    uint8_t toiCount[kMaxPairs];
+    uint64_t toiValid = 0ull, enabled = ~0ull;
+    for (int b = 0; b < nb; ++b) alpha0[b] = 0.0f;
+    for (int i = 0; i < BLCD_MAX_WALLS; ++i) walpha0[i] = 0.0f;
+    for (int k = 0; k < ncl; ++k) { toiCount[clist[k]] = 0; toi[clist[k]] = 1.0f; }
+    for (;;) {
+      int minPair = -1;
+      float minAlpha = 1.0f;
+      for (int k = 0; k < ncl; ++k) {
+        int p = clist[k];
+        if (!((enabled >> p) & 1ull)) continue;
+        if (toiCount[p] > kMaxSubSteps) continue;
+        float alpha = 1.0f;
+        if ((toiValid >> p) & 1ull) {
+          alpha = toi[p];
+        } else {
+          int fa = sc.pair[p].fa, fb = sc.pair[p].fb;
+          if (fa >= nw) continue;          // two non-bullet dynamic bodies
+          int b = fb - nw;
+          if (!is_awake(b)) continue;      // neither side active
+          // put both sweeps on the same interval
+          float al0 = walpha0[fa];
+          if (walpha0[fa] < alpha0[b]) { al0 = alpha0[b]; walpha0[fa] = al0; }
+          else if (alpha0[b] < walpha0[fa]) {
+            al0 = walpha0[fa];
+            Sweep sb = body_sweep(b);
+            sweep_advance(sb, al0);
+            c0[b] = sb.c0; a0[b] = sb.a0; alpha0[b] = sb.alpha0;
+          }
+          Sweep sA;
+          sA.lc = mk(0.0f, 0.0f); sA.c0 = mk(0.0f, 0.0f); sA.c = mk(0.0f, 0.0f); sA.a0 = 0.0f; sA.a = 0.0f; sA.alpha0 = walpha0[fa];
+          float t;
+          ++cnt[BLCD_CNT_TOI_CALLS];
+          int state = time_of_impact(&t, sc.wall[fa], sA, bshape(b), body_sweep(b));
+          if (state == TOI_TOUCHING) alpha = fminb(al0 + (1.0f - al0) * t, 1.0f);
+          else alpha = 1.0f;
+          toi[p] = alpha;
+          toiValid |= 1ull << p;
+        }
+        if (alpha < minAlpha) { minPair = p; minAlpha = alpha; }
+      }
+      if (minPair < 0 || 1.0f - 10.0f * kEps < minAlpha) break;
+      const int wl = sc.pair[minPair].fa, b = sc.pair[minPair].fb - nw;
+      // advance both bodies to the time of impact
+      V2 bk_c0 = c0[b], bk_c = c[b];
+      float bk_a0 = a0[b], bk_a = a[b], bk_alpha0 = alpha0[b], bk_walpha = walpha0[wl];
+      {
+        Sweep sb = body_sweep(b);
+        sweep_advance(sb, minAlpha);
+        c0[b] = sb.c0; a0[b] = sb.a0; alpha0[b] = sb.alpha0;
+        c[b] = sb.c0; a[b] = sb.a0;
+        xf[b] = xf_of(c[b], a[b], lc_of(b));
+        walpha0[wl] = minAlpha;
+      }
+      bool touching = update_contact(minPair);
+      toiValid &= ~(1ull << minPair);
+      ++toiCount[minPair];
+      if (!touching) {
+        enabled &= ~(1ull << minPair);
+        c0[b] = bk_c0; c[b] = bk_c; a0[b] = bk_a0; a[b] = bk_a; alpha0[b] = bk_alpha0; walpha0[wl] = bk_walpha;
+        xf[b] = xf_of(c[b], a[b], lc_of(b));
+        continue;
+      }
+      ++cnt[BLCD_CNT_TOI_EVENTS];
+      set_awake(b);
+      // mini island: body b, the wall, plus the other walls b touches at this pose
+      int ntc = 0;
+      uint32_t wallIn = 1u << wl;
+      uint64_t inIsland = 1ull << minPair;
+      hot.u(sc.h_con + kHotCon * ntc + C_PK) = ((uint32_t)pslot[minPair] << 12);
+      ++ntc;
+      for (int k = 0; k < ncl; ++k) {
+        int p = clist[k];
+        int fa = sc.pair[p].fa, fb = sc.pair[p].fb;
+        if (fb != nw + b && fa != nw + b) continue;
+        if (ntc == sc.maxm) break;
+        if ((inIsland >> p) & 1ull) continue;
+        if (fa >= nw) continue;  // other body dynamic, no bullets: skipped
+        float bkw = walpha0[fa];
+        if (!((wallIn >> fa) & 1u)) walpha0[fa] = minAlpha;
+        bool t2 = update_contact(p);
+        enabled |= 1ull << p;     // b2Contact::Update re-enables
+        if (!t2) { walpha0[fa] = bkw; continue; }
+        inIsland |= 1ull << p;
+        hot.u(sc.h_con + kHotCon * ntc + C_PK) = ((uint32_t)pslot[p] << 12);
+        ++ntc;
+        wallIn |= 1u << fa;
+      }
+      enabled |= 1ull << minPair;
+      // b2Island::SolveTOI
+      float subDt = (1.0f - minAlpha) * h_dt;
+      stage_rows();
+      for (int k = 0; k < ntc; ++k) {  // position constraints only need the packed rows + slot
+        uint32_t pk = hot.u(sc.h_con + kHotCon * k + C_PK);
+        int s = (int)((pk >> 12) & 255u);
+        int p = (int)(g.u(slot_base(s) + S_HDR) & 0xFFu);
+        int fA, fB;
+        pair_ab(p, &fA, &fB);
+        hot.u(sc.h_con + kHotCon * k + C_PK) = (uint32_t)row_of(fA) | ((uint32_t)row_of(fB) << 4) | ((uint32_t)s << 12);
+      }
+      for (int it = 0; it < 20; ++it) {
+        float minSep = 0.0f;
+        for (int k = 0; k < ntc; ++k) minSep = fminb(minSep, contact_solve_position(k, kToiBaumgarte));
+        if (minSep >= -1.5f * kLinearSlop) break;
+      }
+      c0[b] = hc(b); a0[b] = ha(b);  // leap of faith to the new safe state
+      for (int k = 0; k < ntc; ++k) {
+        uint32_t pk = hot.u(sc.h_con + kHotCon * k + C_PK);
+        contact_init(k, (int)((pk >> 12) & 255u), 0, 1.0f, false);
+      }
+      for (int it = 0; it < sc.vel_iters; ++it)
+        for (int k = 0; k < ntc; ++k) contact_solve_velocity(k);
+      {
+        V2 cc = hc(b), vv = hv(b);
+        float aa = ha(b), ww = hw(b);
+        V2 translation = subDt * vv;
+        if (dot(translation, translation) > kMaxTranslationSq) { float ratio = kMaxTranslation / len(translation); vv *= ratio; }
+        float rotation = subDt * ww;
+        if (rotation * rotation > kMaxRotationSq) { float ratio = kMaxRotation / absb(rotation); ww *= ratio; }
+        cc += subDt * vv;
+        aa += subDt * ww;
+        c[b] = cc; a[b] = aa; v[b] = vv; w[b] = ww;
+        xf[b] = xf_of(c[b], a[b], lc_of(b));
+      }
+      // synchronize the broad phase, invalidate the cached TOIs of everything touching the displaced body
+      moved = 0u;
+      sync_fixture(b, xf_of(c0[b], a0[b], lc_of(b)));
+      for (int k = 0; k < ncl; ++k) {
+        int p = clist[k];
+        if (sc.pair[p].fb == nw + b || sc.pair[p].fa == nw + b) toiValid &= ~(1ull << p);
+      }
+      int ncl0 = ncl;
+      find_new_contacts(moved);
+      for (int k = 0; k < ncl - ncl0; ++k) { toiCount[clist[k]] = 0; toi[clist[k]] = 1.0f; toiValid &= ~(1ull << clist[k]); enabled |= 1ull << clist[k]; }
+      moved = 0u;
+    }
+  }
+
+  BLCD_HD Sweep body_sweep(int b) const {
+    Sweep s;
+    s.lc = lc_of(b); s.c0 = c0[b]; s.c = c[b]; s.a0 = a0[b]; s.a = a[b]; s.alpha0 = alpha0[b];
+    return s;
+  }
+
+  // ---- b2World::Step -------------------------------------------------------------------------------------------------
+  BLCD_HD void b2_step() {
+    const float dt = sc.dt;
+    if (newFixture) {
+      find_new_contacts((1u << (sc.nw + sc.nb)) - 1u);
+      newFixture = false;
+    }
+    float dtRatio = inv_dt0 * dt;
+    collide();
+    solve(dt, dtRatio);
+    if (!(sc.flags & BLCD_FLAG_NO_TOI)) solve_toi(dt);
+    inv_dt0 = 1.0f / dt;
+    ++cnt[BLCD_CNT_SUBSTEPS];
+    for (int s = 0; s < sc.maxm; ++s)
+      if ((slotUsed >> s) & 1u) cnt[BLCD_CNT_MANIFOLD_POINTS] += (g.u(slot_base(s) + S_HDR) >> 16) & 0xFFu;
+    cnt[BLCD_CNT_SLEEP_STEPS] += (uint32_t)(sc.nb - popc(awake & ((1u << sc.nb) - 1u)));
+  }
+
+  // WorldEnv.step (world_env.py:431-452): motor speeds from the clipped action, then n_substeps world steps
+  BLCD_HD void env_step(const float* action) {
+    ep_t += 1;
+    for (int j = 0; j < sc.nj; ++j) {
+      const DJoint& jd = sc.joint[j];
+      if (jd.act < 0) continue;
+      double av = (double)action[jd.act];
+      av = av < -1.0 ? -1.0 : (av > 1.0 ? 1.0 : av);
+      set_awake(jd.a);
+      set_awake(jd.b);
+      hot[sc.h_joint + kHotJoint * j + J_MS] = (float)(jd.speed * av);
+    }
+    for (int s = 0; s < sc.nsub; ++s) b2_step();
+  }
+
+  BLCD_HD void draw_action(float* action) {
+    for (int k = 0; k < sc.A; ++k) action[k] = (float)rng.uniform(-1.0, 1.0);
+  }
+
+  // ---- reset (world_env.py:197-385) ----------------------------------------------------------------------------------
+  BLCD_HD static double mapto(double x, double lo, double hi) { return ((x + 1.0) / 2.0 * (hi - lo)) + lo; }
+  BLCD_HD static double rmapto(double x, double lo, double hi) { return ((x - lo) / (hi - lo) * 2.0) + -1.0; }
+
+  // fresh b2World with every dynamic body created at pose[b] = (x, y, angle)
+  BLCD_HD void build_fresh(const float (*pose)[3]) {
+    awake = (1u << sc.nb) - 1u;
+    newFixture = true;
+    inv_dt0 = 0.0f;
+    ep_t = 0;
+    ncl = 0;
+    slotUsed = 0u;
+    moved = 0u;
+    for (int k = 0; k < kMaxPairs; ++k) pslot[k] = -1;
+    for (int s = 0; s < sc.maxm; ++s) g.u(slot_base(s) + S_HDR) = kSlotFree;
+    for (int k = 0; k < BLCD_N_COUNTERS; ++k) cnt[k] = 0u;
+    for (int b = 0; b < BLCD_MAX_BODIES; ++b) {
+      if (b < sc.nb) {
+        Xf t;
+        t.p = mk(pose[b][0], pose[b][1]);
+        t.q = rot_of(pose[b][2]);
+        xf[b] = t;
+        c[b] = xmul(t, lc_of(b)); c0[b] = c[b];
+        a[b] = pose[b][2]; a0[b] = a[b];
+        v[b] = mk(0.0f, 0.0f); w[b] = 0.0f; sleepT[b] = 0.0f; alpha0[b] = 0.0f;
+        Box bb = shape_aabb(bshape(b), t);
+        V2 r = mk(kAabbExtension, kAabbExtension);
+        fat[b].lo = bb.lo - r;
+        fat[b].hi = bb.hi + r;
+      }
+    }
+    for (int j = 0; j < sc.nj; ++j) {
+      int h = sc.h_joint + kHotJoint * j;
+      hot[h + J_IX] = 0.0f; hot[h + J_IY] = 0.0f; hot[h + J_IZ] = 0.0f; hot[h + J_MI] = 0.0f; hot[h + J_MS] = 0.0f;
+      hot.u(h + J_PK) = 0u;
+    }
+  }
+
+  // b2Body::SetTransform
+  BLCD_HD void set_transform(int b, V2 position, float angle) {
+    Xf t;
+    t.q = rot_of(angle);
+    t.p = position;
+    xf[b] = t;
+    c[b] = xmul(t, lc_of(b)); a[b] = angle;
+    c0[b] = c[b]; a0[b] = angle;
+    sync_fixture(b, t);
+  }
+
+  BLCD_HDN void reset(const float* full_state) {
+    float pose[BLCD_MAX_BODIES][3];
+    double angle64[BLCD_MAX_BODIES];
+    const double W = sc.world_w, H = sc.world_h;
+    variant = 0u;
+    for (int b = 0; b < sc.nb; ++b) {
+      const DBody& bd = sc.body[b];
+      if (bd.role == BLCD_ROLE_ROOT) {
+        double rangex = 1.0 - (2.0 * bd.extent / W), rangey = 1.0 - (2.0 * bd.extent / H);
+        double x = mapto(rng.uniform(-rangex, rangex), 0.0, W);
+        double y = mapto(rng.uniform(-rangey, -rangey), 0.0, H);
+        double s = mapto(rng.uniform(-1.0, 1.0), -1.0, 1.0);
+        double cc = mapto(rng.uniform(-1.0, 1.0), -1.0, 1.0);
+        double ang = atan2(s, cc);
+        if (!bd.rand_angle) ang = 0.0;
+        angle64[b] = ang;
+        pose[b][0] = (float)x; pose[b][1] = (float)y; pose[b][2] = (float)ang;
+      } else if (bd.role == BLCD_ROLE_CHILD) {
+        double mangle = angle64[bd.root] + bd.joint_angle;
+        mangle = atan2(sin(mangle), cos(mangle));
+        angle64[b] = mangle;
+        double pangle = angle64[bd.parent];
+        double aax = cos(pangle) * bd.anchor_a[0] - sin(pangle) * bd.anchor_a[1];
+        double aay = sin(pangle) * bd.anchor_a[0] + cos(pangle) * bd.anchor_a[1];
+        double abx = cos(mangle) * bd.anchor_b[0] - sin(mangle) * bd.anchor_b[1];
+        double aby = sin(mangle) * bd.anchor_b[0] + cos(mangle) * bd.anchor_b[1];
+        float px = pose[bd.parent][0] + (float)aax, py = pose[bd.parent][1] + (float)aay;
+        px = px - (float)abx; py = py - (float)aby;
+        pose[b][0] = px; pose[b][1] = py; pose[b][2] = (float)mangle;
+      } else {
+        if (bd.nvar > 1) variant |= (rng.next() & 1u) << b;
+        double rangex = 1.0 - (2.0 * bd.extent / W), rangey = 1.0 - (2.0 * bd.extent / H);
+        double x = mapto(rng.uniform(-rangex, rangex), 0.0, W);
+        double y = sc.has_robot ? mapto(rng.uniform(-rangey, -0.25), 0.0, H) : mapto(rng.uniform(-rangey, rangey), 0.0, H);
+        double ang = 0.0;
+        if (bd.rand_angle) {
+          double s = mapto(rng.uniform(-1.0, 1.0), -1.0, 1.0);
+          double cc = mapto(rng.uniform(-1.0, 1.0), -1.0, 1.0);
+          ang = atan2(s, cc);
+        }
+        pose[b][0] = (float)x; pose[b][1] = (float)y; pose[b][2] = (float)ang;
+      }
+    }
+    build_fresh(pose);
+    if (full_state) {
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int b = 0; b < sc.nb; ++b) {
+          const DBody& bd = sc.body[b];
+          if ((bd.role == BLCD_ROLE_OBJECT) != (pass == 0)) continue;
+          double x = mapto((double)full_state[bd.obs[0]], 0.0, W);
+          double y = mapto((double)full_state[bd.obs[1]], 0.0, H);
+          double ang = atan2((double)full_state[bd.obs[3]], (double)full_state[bd.obs[2]]);
+          set_transform(b, mk((float)x, (float)y), a[b]);
+          set_transform(b, xf[b].p, (float)ang);
+        }
+      }
+      moved = 0u;
+    }
+  }
+
+  // ---- observation (world_env.py:387-429, 460-512) -------------------------------------------------------------------
+  BLCD_HD void obs_body(int b, float out[4]) const {
+    out[0] = (float)rmapto((double)xf[b].p.x, 0.0, (double)sc.world_w);
+    out[1] = (float)rmapto((double)xf[b].p.y, 0.0, (double)sc.world_h);
+    out[2] = (float)cos((double)a[b]);
+    out[3] = (float)sin((double)a[b]);
+  }
+
+  BLCD_HD uint32_t lcd_row(int R) const {  // output row R (0 = top of the world)
+    int y = sc.lcd_h - 1 - R;
+    uint32_t ink = 0u;
+    for (int b = 0; b < sc.nb; ++b)
+      ink |= body_row(bshape(b), xf[b].p.x, xf[b].p.y, xf[b].q.s, xf[b].q.c, y, sc.world_w, sc.lcd_w, sc.lcd_h, sc.rules);
+    return row_bits_from_ink(ink, sc.lcd_w);
+  }
+};
+
+}  // namespace blcd

@@ -1,0 +1,549 @@
+// boxlcd_b200.cu -- CUDA kernels (sm_100a) and the C ABI of libboxlcd_b200.so (include/boxlcd_b200.h).
+//
+// Kernels (one thread per world unless noted; shared memory laid out [word][thread], see blcd_world.cuh):
+//   k_init          mark all manifold slots free after the state buffer was zeroed
+//   k_reset         WorldEnv.reset          (world_env.py:306-385)
+//   k_set_bodies    fresh world at given poses / velocities (single-step parity protocol)
+//   k_step          WorldEnv.step           (world_env.py:431-458), optionally followed by _get_obs
+//   k_rollout       examples/collect.py:31-39 inner loop, T steps per launch, actions from the per-world Philox stream
+//   k_observe       WorldEnv._get_obs       (world_env.py:387-429)
+//   k_render_poses  WorldEnv.lcd_render     (world_env.py:460-512), one thread per (world, frame row)
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include "blcd_world.cuh"
+
+using namespace blcd;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(const std::string& msg) { g_err = msg; return -1; }
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));              \
+  } while (0)
+
+struct OutPtrs {
+  float* full_state;   // [N, S] or [N, T, S]
+  float* proprio;      // [N, P]
+  uint32_t* lcd_bits;  // [N, H] or [N, T, H]
+  uint8_t* lcd_bool;   // [N, H, W]
+  uint8_t* done;       // [N]
+  float* actions;      // [N, A] or [N, T, A]
+};
+
+template <int BLOCK>
+__device__ __forceinline__ const DScene& stage_scene(const DScene* scene_g, unsigned char* smem_raw) {
+  // the scene table is read by every thread with divergent indices: keep one copy per block in shared memory
+  DScene* sc = reinterpret_cast<DScene*>(smem_raw);
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(scene_g);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(sc);
+  for (int i = threadIdx.x; i < (int)(sizeof(DScene) / 4); i += BLOCK) dst[i] = src[i];
+  __syncthreads();
+  return *sc;
+}
+
+constexpr int kSceneBytes = (int)((sizeof(DScene) + 15) / 16 * 16);
+
+template <int BLOCK>
+__device__ __forceinline__ float* hot_base(unsigned char* smem_raw) {
+  return reinterpret_cast<float*>(smem_raw + kSceneBytes) + threadIdx.x;
+}
+
+template <int BLOCK>
+__device__ __forceinline__ void write_obs(const Sim<BLOCK>& sim, const DScene& sc, const OutPtrs& o, int64_t row) {
+  // row = world index (or world * T + t for rollouts)
+  if (o.full_state || o.proprio) {
+    float fs[BLCD_MAX_OBS];
+    for (int b = 0; b < BLCD_MAX_BODIES; ++b) {
+      if (b < sc.nb) {
+        float ob[4];
+        sim.obs_body(b, ob);
+        for (int k = 0; k < 4; ++k) fs[sc.body[b].obs[k]] = ob[k];
+      }
+    }
+    if (o.full_state)
+      for (int i = 0; i < sc.S; ++i) o.full_state[row * sc.S + i] = fs[i];
+    if (o.proprio) {
+      if (sc.P == 0) o.proprio[row] = 0.0f;
+      for (int i = 0; i < sc.P; ++i) o.proprio[row * sc.P + i] = fs[sc.pobs[i]];
+    }
+  }
+  if (o.lcd_bits || o.lcd_bool) {
+    for (int R = 0; R < sc.lcd_h; ++R) {
+      uint32_t bits = sim.lcd_row(R);
+      if (o.lcd_bits) o.lcd_bits[row * sc.lcd_h + R] = bits;
+      if (o.lcd_bool)
+        for (int x = 0; x < sc.lcd_w; ++x) o.lcd_bool[(row * sc.lcd_h + R) * sc.lcd_w + x] = (uint8_t)((bits >> x) & 1u);
+    }
+  }
+  if (o.done) o.done[row] = (uint8_t)(sim.ep_t >= sc.ep_len);
+}
+
+__global__ void k_init(const DScene* scene_g, uint32_t* state, int64_t n) {
+  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n) return;
+  for (int s = 0; s < scene_g->maxm; ++s) state[(int64_t)(scene_g->off_slots + kSlotWords * s) * n + w] = kSlotFree;
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_reset(const DScene* scene_g, uint32_t* state, int64_t n, uint64_t seed, int64_t world_offset,
+                                                  const int64_t* idx, int64_t n_idx, const float* full_state) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const DScene& sc = stage_scene<BLOCK>(scene_g, smem_raw);
+  int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= n_idx) return;
+  int64_t w = idx ? idx[i] : i;
+  if (w < 0 || w >= n) return;
+  Sim<BLOCK> sim(sc, hot_base<BLOCK>(smem_raw), state, n, w);
+  sim.load(seed, world_offset + w);
+  float fs[BLCD_MAX_OBS];
+  if (full_state)
+    for (int k = 0; k < sc.S; ++k) fs[k] = full_state[i * sc.S + k];
+  sim.reset(full_state ? fs : nullptr);
+  sim.store();
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_set_bodies(const DScene* scene_g, uint32_t* state, int64_t n, uint64_t seed, int64_t world_offset,
+                                                       const float* bodies, const uint32_t* variants) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const DScene& sc = stage_scene<BLOCK>(scene_g, smem_raw);
+  int64_t w = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (w >= n) return;
+  Sim<BLOCK> sim(sc, hot_base<BLOCK>(smem_raw), state, n, w);
+  sim.load(seed, world_offset + w);
+  sim.variant = variants ? (variants[w] & 0xFFu) : 0u;
+  float pose[BLCD_MAX_BODIES][3];
+  const float* src = bodies + w * sc.nb * BLCD_BODY_STATE;
+  for (int b = 0; b < sc.nb; ++b) { pose[b][0] = src[b * 6]; pose[b][1] = src[b * 6 + 1]; pose[b][2] = src[b * 6 + 2]; }
+  sim.build_fresh(pose);
+  for (int b = 0; b < sc.nb; ++b) { sim.v[b] = mk(src[b * 6 + 3], src[b * 6 + 4]); sim.w[b] = src[b * 6 + 5]; }
+  sim.store();
+}
+
+__global__ void k_get_bodies(const DScene* scene_g, const uint32_t* state, int64_t n, float* bodies) {
+  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n) return;
+  const DScene& sc = *scene_g;
+  const float* sf = reinterpret_cast<const float*>(state);
+  for (int b = 0; b < sc.nb; ++b) {
+    int o = kBodyWords * b;
+    float a = sf[(int64_t)(o + 2) * n + w];
+    float* dst = bodies + (w * sc.nb + b) * BLCD_BODY_STATE;
+    dst[0] = sf[(int64_t)(o + 11) * n + w]; dst[1] = sf[(int64_t)(o + 12) * n + w]; dst[2] = a;
+    dst[3] = sf[(int64_t)(o + 3) * n + w]; dst[4] = sf[(int64_t)(o + 4) * n + w]; dst[5] = sf[(int64_t)(o + 5) * n + w];
+  }
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_step(const DScene* scene_g, uint32_t* state, int64_t n, uint64_t seed, int64_t world_offset,
+                                                 const float* actions, int n_steps, OutPtrs out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const DScene& sc = stage_scene<BLOCK>(scene_g, smem_raw);
+  int64_t w = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (w >= n) return;
+  Sim<BLOCK> sim(sc, hot_base<BLOCK>(smem_raw), state, n, w);
+  sim.load(seed, world_offset + w);
+  float act[BLCD_MAX_OBS];
+  for (int t = 0; t < n_steps; ++t) {
+    if (actions) { for (int k = 0; k < sc.A; ++k) act[k] = actions[w * sc.A + k]; }
+    else sim.draw_action(act);
+    if (out.actions)
+      for (int k = 0; k < sc.A; ++k) out.actions[w * sc.A + k] = act[k];
+    sim.env_step(act);
+  }
+  OutPtrs o = out;
+  o.actions = nullptr;
+  write_obs<BLOCK>(sim, sc, o, w);
+  sim.store();
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_rollout(const DScene* scene_g, uint32_t* state, int64_t n, uint64_t seed, int64_t world_offset,
+                                                    int T, OutPtrs out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const DScene& sc = stage_scene<BLOCK>(scene_g, smem_raw);
+  int64_t w = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (w >= n) return;
+  Sim<BLOCK> sim(sc, hot_base<BLOCK>(smem_raw), state, n, w);
+  sim.load(seed, world_offset + w);
+  float act[BLCD_MAX_OBS];
+  for (int t = 0; t < T; ++t) {
+    int64_t row = w * T + t;
+    write_obs<BLOCK>(sim, sc, out, row);   // obs_t is recorded before action t (collect.py:33-39)
+    sim.draw_action(act);
+    if (out.actions)
+      for (int k = 0; k < sc.A; ++k) out.actions[row * sc.A + k] = act[k];
+    sim.env_step(act);
+  }
+  sim.store();
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_observe(const DScene* scene_g, uint32_t* state, int64_t n, OutPtrs out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const DScene& sc = stage_scene<BLOCK>(scene_g, smem_raw);
+  int64_t w = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (w >= n) return;
+  Sim<BLOCK> sim(sc, hot_base<BLOCK>(smem_raw), state, n, w);
+  sim.load(0, 0);
+  write_obs<BLOCK>(sim, sc, out, w);
+}
+
+// one thread per (world, frame row): lanes 0..H-1 of consecutive worlds write consecutive words -> coalesced stores
+__global__ void __launch_bounds__(256) k_render_poses(const DScene* scene_g, const float* poses, const uint32_t* variants, int64_t n,
+                                                       int lcd_w, int lcd_h, uint32_t* bits) {
+  __shared__ DScene sc_s;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(scene_g);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sc_s);
+    for (int i = threadIdx.x; i < (int)(sizeof(DScene) / 4); i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+  }
+  const DScene& sc = sc_s;
+  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n * lcd_h) return;
+  int64_t w = gid / lcd_h;
+  int R = (int)(gid - w * lcd_h);
+  int y = lcd_h - 1 - R;
+  uint32_t variant = variants ? variants[w] : 0u;
+  uint32_t ink = 0u;
+  for (int b = 0; b < sc.nb; ++b) {
+    const float* p = poses + (w * sc.nb + b) * 4;
+    ink |= body_row(sc.body[b].shape[(variant >> b) & 1u], p[0], p[1], p[2], p[3], y, sc.world_w, lcd_w, lcd_h, sc.rules);
+  }
+  bits[gid] = row_bits_from_ink(ink, lcd_w);
+}
+
+}  // namespace
+
+struct blcd_env {
+  DScene scene;
+  DScene* scene_dev = nullptr;
+  uint32_t* state = nullptr;
+  int64_t n = 0, world_offset = 0;
+  uint64_t seed = 0;
+  int device = 0, block = 64;
+  int64_t launches = 0;
+  bool timing = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_ms = -1.0f;
+  // pinned staging for blcd_step_host
+  float* h_act = nullptr; float* h_fs = nullptr; uint32_t* h_bits = nullptr; uint8_t* h_done = nullptr;
+  float* d_act = nullptr; float* d_fs = nullptr; uint32_t* d_bits = nullptr; uint8_t* d_done = nullptr;
+};
+
+namespace {
+
+size_t smem_bytes(const blcd_env* h, int block) { return (size_t)kSceneBytes + (size_t)h->scene.hot_words * block * sizeof(float); }
+
+template <typename F>
+int launch_sized(blcd_env* h, F f) {
+  switch (h->block) {
+    case 32: return f(std::integral_constant<int, 32>());
+    case 64: return f(std::integral_constant<int, 64>());
+    case 128: return f(std::integral_constant<int, 128>());
+    default: return fail("unsupported block size");
+  }
+}
+
+template <typename K>
+int set_smem_attr(K kernel, size_t bytes) {
+  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+int begin_timing(blcd_env* h, cudaStream_t st) {
+  if (h->timing) CK(cudaEventRecord(h->ev0, st));
+  return 0;
+}
+int end_timing(blcd_env* h, cudaStream_t st) {
+  if (h->timing) { CK(cudaEventRecord(h->ev1, st)); h->last_ms = -2.0f; }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* blcd_last_error(void) { return g_err.c_str(); }
+int blcd_version(void) { return 100; }
+
+int blcd_create(const blcd_spec* spec_host, int64_t n_worlds, int device, uint64_t seed, int64_t world_offset, blcd_handle* out) {
+  if (!spec_host || !out || n_worlds <= 0) return fail("blcd_create: bad arguments");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail("blcd_create: no such CUDA device");
+  CK(cudaSetDevice(device));
+  blcd_env* h = new blcd_env();
+  // manifold slots per world: enough for every touching pair seen in long random rollouts of the reference scenes
+  // (tests/test_hostsim_vs_oracle.py measures it); overflow is counted in BLCD_CNT_OVERFLOW, never silent
+  int maxm = spec_host->n_bodies <= 2 ? 4 : (spec_host->n_bodies <= 4 ? 6 : (spec_host->n_bodies == 5 ? 8 : 16));
+  if (const char* e = getenv("BLCD_MAX_MANIFOLDS")) maxm = atoi(e);
+  if (maxm < 1 || maxm > 16) { delete h; return fail("BLCD_MAX_MANIFOLDS must be in 1..16"); }
+  const char* err = host::build_scene(h->scene, *spec_host, maxm);
+  if (err) { delete h; return fail(std::string("blcd_create: ") + err); }
+  h->n = n_worlds; h->device = device; h->seed = seed; h->world_offset = world_offset;
+  // block size: largest of 128/64/32 that still lets several blocks share an SM's shared memory
+  int smem_max = 0;
+  CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  h->block = 64;
+  if (const char* e = getenv("BLCD_BLOCK")) h->block = atoi(e);
+  while (h->block > 32 && smem_bytes(h, h->block) > (size_t)smem_max) h->block /= 2;
+  if (smem_bytes(h, h->block) > (size_t)smem_max) { delete h; return fail("scene working set does not fit shared memory"); }
+  CK(cudaMalloc(&h->scene_dev, sizeof(DScene)));
+  CK(cudaMemcpy(h->scene_dev, &h->scene, sizeof(DScene), cudaMemcpyHostToDevice));
+  size_t bytes = (size_t)h->scene.state_words * (size_t)n_worlds * 4;
+  CK(cudaMalloc(&h->state, bytes));
+  CK(cudaMemset(h->state, 0, bytes));
+  k_init<<<(unsigned)((n_worlds + 255) / 256), 256>>>(h->scene_dev, h->state, n_worlds);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  h->launches += 1;
+  CK(cudaEventCreate(&h->ev0));
+  CK(cudaEventCreate(&h->ev1));
+  int rc = launch_sized(h, [&](auto B) {
+    constexpr int BLOCK = decltype(B)::value;
+    size_t sb = smem_bytes(h, BLOCK);
+    if (set_smem_attr(k_reset<BLOCK>, sb)) return -1;
+    if (set_smem_attr(k_set_bodies<BLOCK>, sb)) return -1;
+    if (set_smem_attr(k_step<BLOCK>, sb)) return -1;
+    if (set_smem_attr(k_rollout<BLOCK>, sb)) return -1;
+    if (set_smem_attr(k_observe<BLOCK>, sb)) return -1;
+    return 0;
+  });
+  if (rc) return rc;
+  *out = h;
+  return 0;
+}
+
+int blcd_destroy(blcd_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaFree(h->scene_dev);
+  cudaFree(h->state);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->h_act) cudaFreeHost(h->h_act);
+  if (h->h_fs) cudaFreeHost(h->h_fs);
+  if (h->h_bits) cudaFreeHost(h->h_bits);
+  if (h->h_done) cudaFreeHost(h->h_done);
+  cudaFree(h->d_act); cudaFree(h->d_fs); cudaFree(h->d_bits); cudaFree(h->d_done);
+  delete h;
+  return 0;
+}
+
+int blcd_reset(blcd_handle h, const int64_t* idx_dev, int64_t n, const float* full_state_dev, uint64_t stream) {
+  if (!h) return fail("blcd_reset: null handle");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t cnt = idx_dev ? n : h->n;
+  if (cnt <= 0) return 0;
+  int rc = launch_sized(h, [&](auto B) {
+    constexpr int BLOCK = decltype(B)::value;
+    k_reset<BLOCK><<<(unsigned)((cnt + BLOCK - 1) / BLOCK), BLOCK, smem_bytes(h, BLOCK), st>>>(h->scene_dev, h->state, h->n, h->seed, h->world_offset,
+                                                                                              idx_dev, cnt, full_state_dev);
+    return 0;
+  });
+  if (rc) return rc;
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+int blcd_set_bodies(blcd_handle h, const float* bodies_dev, const uint32_t* variant_dev, uint64_t stream) {
+  if (!h || !bodies_dev) return fail("blcd_set_bodies: bad arguments");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = launch_sized(h, [&](auto B) {
+    constexpr int BLOCK = decltype(B)::value;
+    k_set_bodies<BLOCK><<<(unsigned)((h->n + BLOCK - 1) / BLOCK), BLOCK, smem_bytes(h, BLOCK), st>>>(h->scene_dev, h->state, h->n, h->seed, h->world_offset,
+                                                                                                     bodies_dev, variant_dev);
+    return 0;
+  });
+  if (rc) return rc;
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+int blcd_get_bodies(blcd_handle h, float* bodies_dev, uint64_t stream) {
+  if (!h || !bodies_dev) return fail("blcd_get_bodies: bad arguments");
+  CK(cudaSetDevice(h->device));
+  k_get_bodies<<<(unsigned)((h->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(h->scene_dev, h->state, h->n, bodies_dev);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+static int step_impl(blcd_handle h, const float* actions_dev, int n_steps, OutPtrs out, cudaStream_t st) {
+  if (begin_timing(h, st)) return -1;
+  int rc = launch_sized(h, [&](auto B) {
+    constexpr int BLOCK = decltype(B)::value;
+    k_step<BLOCK><<<(unsigned)((h->n + BLOCK - 1) / BLOCK), BLOCK, smem_bytes(h, BLOCK), st>>>(h->scene_dev, h->state, h->n, h->seed, h->world_offset,
+                                                                                               actions_dev, n_steps, out);
+    return 0;
+  });
+  if (rc) return rc;
+  CK(cudaGetLastError());
+  if (end_timing(h, st)) return -1;
+  h->launches += 1;
+  return 0;
+}
+
+int blcd_step(blcd_handle h, const float* actions_dev, float* actions_out_dev, uint64_t stream) {
+  if (!h) return fail("blcd_step: null handle");
+  CK(cudaSetDevice(h->device));
+  OutPtrs out = {nullptr, nullptr, nullptr, nullptr, nullptr, actions_out_dev};
+  return step_impl(h, actions_dev, 1, out, (cudaStream_t)stream);
+}
+
+int blcd_step_observe(blcd_handle h, const float* actions_dev, float* actions_out_dev, float* full_state_dev, float* proprio_dev,
+                      uint32_t* lcd_bits_dev, uint8_t* lcd_bool_dev, uint8_t* done_dev, uint64_t stream) {
+  if (!h) return fail("blcd_step_observe: null handle");
+  CK(cudaSetDevice(h->device));
+  OutPtrs out = {full_state_dev, proprio_dev, lcd_bits_dev, lcd_bool_dev, done_dev, actions_out_dev};
+  return step_impl(h, actions_dev, 1, out, (cudaStream_t)stream);
+}
+
+int blcd_observe(blcd_handle h, float* full_state_dev, float* proprio_dev, uint32_t* lcd_bits_dev, uint8_t* lcd_bool_dev, uint8_t* done_dev,
+                 uint64_t stream) {
+  if (!h) return fail("blcd_observe: null handle");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  OutPtrs out = {full_state_dev, proprio_dev, lcd_bits_dev, lcd_bool_dev, done_dev, nullptr};
+  int rc = launch_sized(h, [&](auto B) {
+    constexpr int BLOCK = decltype(B)::value;
+    k_observe<BLOCK><<<(unsigned)((h->n + BLOCK - 1) / BLOCK), BLOCK, smem_bytes(h, BLOCK), st>>>(h->scene_dev, h->state, h->n, out);
+    return 0;
+  });
+  if (rc) return rc;
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+int blcd_rollout(blcd_handle h, int32_t T, float* full_state_dev, uint32_t* lcd_bits_dev, float* actions_dev, uint64_t stream) {
+  if (!h || T <= 0) return fail("blcd_rollout: bad arguments");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  OutPtrs out = {full_state_dev, nullptr, lcd_bits_dev, nullptr, nullptr, actions_dev};
+  if (begin_timing(h, st)) return -1;
+  int rc = launch_sized(h, [&](auto B) {
+    constexpr int BLOCK = decltype(B)::value;
+    k_rollout<BLOCK><<<(unsigned)((h->n + BLOCK - 1) / BLOCK), BLOCK, smem_bytes(h, BLOCK), st>>>(h->scene_dev, h->state, h->n, h->seed, h->world_offset, T, out);
+    return 0;
+  });
+  if (rc) return rc;
+  CK(cudaGetLastError());
+  if (end_timing(h, st)) return -1;
+  h->launches += 1;
+  return 0;
+}
+
+int blcd_step_host(blcd_handle h, const float* actions_host, float* full_state_host, uint32_t* lcd_bits_host, uint8_t* done_host) {
+  if (!h) return fail("blcd_step_host: null handle");
+  CK(cudaSetDevice(h->device));
+  const DScene& sc = h->scene;
+  size_t na = (size_t)h->n * sc.A * 4, nf = (size_t)h->n * sc.S * 4, nb = (size_t)h->n * sc.lcd_h * 4, nd = (size_t)h->n;
+  if (!h->d_act) {
+    CK(cudaMalloc(&h->d_act, na)); CK(cudaMalloc(&h->d_fs, nf)); CK(cudaMalloc(&h->d_bits, nb)); CK(cudaMalloc(&h->d_done, nd));
+    CK(cudaMallocHost(&h->h_act, na)); CK(cudaMallocHost(&h->h_fs, nf)); CK(cudaMallocHost(&h->h_bits, nb)); CK(cudaMallocHost(&h->h_done, nd));
+  }
+  cudaStream_t st = 0;
+  if (actions_host) {
+    memcpy(h->h_act, actions_host, na);
+    CK(cudaMemcpyAsync(h->d_act, h->h_act, na, cudaMemcpyHostToDevice, st));
+  }
+  OutPtrs out = {full_state_host ? h->d_fs : nullptr, nullptr, lcd_bits_host ? h->d_bits : nullptr, nullptr, done_host ? h->d_done : nullptr, nullptr};
+  if (step_impl(h, actions_host ? h->d_act : nullptr, 1, out, st)) return -1;
+  if (full_state_host) CK(cudaMemcpyAsync(h->h_fs, h->d_fs, nf, cudaMemcpyDeviceToHost, st));
+  if (lcd_bits_host) CK(cudaMemcpyAsync(h->h_bits, h->d_bits, nb, cudaMemcpyDeviceToHost, st));
+  if (done_host) CK(cudaMemcpyAsync(h->h_done, h->d_done, nd, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (full_state_host) memcpy(full_state_host, h->h_fs, nf);
+  if (lcd_bits_host) memcpy(lcd_bits_host, h->h_bits, nb);
+  if (done_host) memcpy(done_host, h->h_done, nd);
+  return 0;
+}
+
+int blcd_render_poses(blcd_handle h, const float* poses_dev, const uint32_t* variant_dev, int64_t n, uint32_t* lcd_bits_dev, uint64_t stream) {
+  return blcd_render_poses_sized(h, poses_dev, variant_dev, n, 0, 0, lcd_bits_dev, stream);
+}
+
+int blcd_render_poses_sized(blcd_handle h, const float* poses_dev, const uint32_t* variant_dev, int64_t n, int32_t lcd_w, int32_t lcd_h,
+                            uint32_t* lcd_bits_dev, uint64_t stream) {
+  if (!h || !poses_dev || !lcd_bits_dev || n < 0) return fail("blcd_render_poses: bad arguments");
+  if (n == 0) return 0;
+  if (lcd_w <= 0) lcd_w = h->scene.lcd_w;
+  if (lcd_h <= 0) lcd_h = h->scene.lcd_h;
+  if (lcd_w > 32) return fail("blcd_render_poses: frame width > 32 needs the tiled path (not built)");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t total = n * lcd_h;
+  if (begin_timing(h, st)) return -1;
+  k_render_poses<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(h->scene_dev, poses_dev, variant_dev, n, lcd_w, lcd_h, lcd_bits_dev);
+  CK(cudaGetLastError());
+  if (end_timing(h, st)) return -1;
+  h->launches += 1;
+  return 0;
+}
+
+int64_t blcd_state_bytes(blcd_handle h) { return h ? (int64_t)h->scene.state_words * h->n * 4 : -1; }
+
+int blcd_save_state(blcd_handle h, void* buf_dev, uint64_t stream) {
+  if (!h || !buf_dev) return fail("blcd_save_state: bad arguments");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(buf_dev, h->state, (size_t)blcd_state_bytes(h), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+int blcd_load_state(blcd_handle h, const void* buf_dev, uint64_t stream) {
+  if (!h || !buf_dev) return fail("blcd_load_state: bad arguments");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(h->state, buf_dev, (size_t)blcd_state_bytes(h), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+int64_t blcd_num_worlds(blcd_handle h) { return h ? h->n : -1; }
+int64_t blcd_kernel_launches(blcd_handle h) { return h ? h->launches : -1; }
+
+int blcd_enable_timing(blcd_handle h, int on) {
+  if (!h) return fail("blcd_enable_timing: null handle");
+  h->timing = on != 0;
+  return 0;
+}
+
+int blcd_last_step_ms(blcd_handle h, float* ms_out) {
+  if (!h || !ms_out) return fail("blcd_last_step_ms: bad arguments");
+  if (!h->timing || h->last_ms == -1.0f) return fail("blcd_last_step_ms: timing not enabled or nothing timed yet");
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventSynchronize(h->ev1));
+  CK(cudaEventElapsedTime(ms_out, h->ev0, h->ev1));
+  return 0;
+}
+
+int blcd_get_counters(blcd_handle h, uint32_t* counters_dev, uint64_t stream) {
+  if (!h || !counters_dev) return fail("blcd_get_counters: bad arguments");
+  CK(cudaSetDevice(h->device));
+  // counters are BLCD_N_COUNTERS consecutive [word][world] rows: transpose with a strided 2-D copy
+  for (int k = 0; k < BLCD_N_COUNTERS; ++k)
+    CK(cudaMemcpy2DAsync(counters_dev + k, BLCD_N_COUNTERS * 4, h->state + (size_t)(h->scene.off_cnt + k) * h->n, 4, 4, (size_t)h->n,
+                         cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+int blcd_scene_info(blcd_handle h, int32_t* out16) {
+  if (!h || !out16) return fail("blcd_scene_info: bad arguments");
+  const DScene& sc = h->scene;
+  int32_t v[16] = {sc.nb, sc.nj, sc.nw, sc.np, sc.S, sc.P, sc.A, sc.lcd_w, sc.lcd_h, sc.maxm, sc.state_words, sc.hot_words, h->block,
+                   (int32_t)smem_bytes(h, h->block), 0, 0};
+  memcpy(out16, v, sizeof(v));
+  return 0;
+}
+
+}  // extern "C"

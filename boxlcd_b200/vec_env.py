@@ -1,0 +1,185 @@
+"""`VecWorldEnv`: N worlds of one scene, resident on one GPU, behind the call shape the reference's vector wrapper
+exposes (research/wrappers/async_vector_env.py:131-242: `reset(idxs, **kwargs)`, `step(actions)` -> (dict of [N, ...]
+arrays, rew[N], done[N], infos), `action_space.sample()`), plus device-tensor entry points for callers that keep their
+data on the GPU.  PyTorch only owns the tensors and the stream; every operation is a call into libboxlcd_b200
+(include/boxlcd_b200.h).  No CPU fallback."""
+import ctypes as C
+import numpy as np
+import torch
+from boxlcd_b200 import _lib, spaces
+
+COUNTER_NAMES = ['contacts', 'pos_iters', 'toi_events', 'toi_calls', 'sleep_steps', 'overflow', 'manifold_points', 'substeps']
+
+
+def _ptr(t):
+  return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class VecWorldEnv:
+  def __init__(self, env, num_envs, device=None, seed=0, world_offset=0):
+    """env: a boxlcd_b200 WorldEnv (scene + config); num_envs worlds are created on `device` (default cuda:current)."""
+    if not torch.cuda.is_available():
+      raise RuntimeError('boxlcd_b200 needs a CUDA device: the simulator only exists as sm_100a kernels (no CPU fallback)')
+    self.env = env
+    self.spec = env.layout.spec
+    self.num_envs = self.n = int(num_envs)
+    self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    if self.device.index is None:
+      self.device = torch.device('cuda', torch.cuda.current_device())
+    self.l = _lib.lib()
+    h = C.c_void_p()
+    _lib.check(self.l.blcd_create(C.byref(self.spec), self.n, self.device.index, int(seed or 0), int(world_offset), C.byref(h)))
+    self.h = h
+    sp = self.spec
+    self.B, self.S, self.A, self.P = sp.n_bodies, sp.obs_size, sp.act_size, max(sp.pobs_size, 1)
+    self.H, self.W = sp.lcd_h, sp.lcd_w
+    self.observation_space = env.observation_space
+    self.single_action_space = env.action_space
+    self.action_space = spaces.Box(-1, 1, (self.n, self.A), dtype=np.float32)
+    f32 = dict(dtype=torch.float32, device=self.device)
+    self._fs = torch.empty((self.n, self.S), **f32)
+    self._pr = torch.empty((self.n, self.P), **f32)
+    self._bits = torch.empty((self.n, self.H), dtype=torch.int32, device=self.device)
+    self._done = torch.empty((self.n,), dtype=torch.uint8, device=self.device)
+    self._act = torch.empty((self.n, self.A), **f32)
+
+  # -- lifetime -------------------------------------------------------------------------------------------------------
+  def close(self):
+    if getattr(self, 'h', None):
+      self.l.blcd_destroy(self.h)
+      self.h = None
+
+  __del__ = close
+
+  def _stream(self):
+    return torch.cuda.current_stream(self.device).cuda_stream
+
+  def info(self):
+    out = (C.c_int32 * 16)()
+    _lib.check(self.l.blcd_scene_info(self.h, out))
+    keys = ['n_bodies', 'n_joints', 'n_walls', 'n_pairs', 'obs_size', 'pobs_size', 'act_size', 'lcd_w', 'lcd_h', 'manifold_slots',
+            'state_words', 'smem_words_per_world', 'block', 'smem_bytes_per_block']
+    return dict(zip(keys, list(out)))
+
+  @property
+  def kernel_launches(self):
+    return int(self.l.blcd_kernel_launches(self.h))
+
+  # -- device-tensor API ------------------------------------------------------------------------------------------------
+  def reset_dev(self, idx=None, full_state=None):
+    """idx: int64 device tensor of world indices (None = all); full_state: [len(idx) or N, S] float32 device tensor"""
+    n = 0 if idx is None else idx.numel()
+    _lib.check(self.l.blcd_reset(self.h, _ptr(idx), n, _ptr(full_state), self._stream()))
+
+  def step_dev(self, actions=None, observe=True):
+    """actions: [N, A] float32 device tensor, or None to draw U[-1,1) actions from the per-world device RNG.
+    Returns (obs dict of device tensors or None, actions used)."""
+    if observe:
+      _lib.check(self.l.blcd_step_observe(self.h, _ptr(actions), _ptr(self._act), _ptr(self._fs), _ptr(self._pr), _ptr(self._bits), None,
+                                          _ptr(self._done), self._stream()))
+      return {'full_state': self._fs, 'proprio': self._pr, 'lcd_bits': self._bits, 'done': self._done}, self._act
+    _lib.check(self.l.blcd_step(self.h, _ptr(actions), _ptr(self._act), self._stream()))
+    return None, self._act
+
+  def observe_dev(self, lcd_bool=None):
+    _lib.check(self.l.blcd_observe(self.h, _ptr(self._fs), _ptr(self._pr), _ptr(self._bits), _ptr(lcd_bool), _ptr(self._done), self._stream()))
+    return {'full_state': self._fs, 'proprio': self._pr, 'lcd_bits': self._bits, 'done': self._done}
+
+  def rollout_dev(self, T, full_state=None, lcd_bits=None, actions=None):
+    """collect.py's inner loop for all worlds, T steps in one launch.  Output tensors [N, T, ...] are allocated if not given."""
+    f32 = dict(dtype=torch.float32, device=self.device)
+    full_state = torch.empty((self.n, T, self.S), **f32) if full_state is None else full_state
+    lcd_bits = torch.empty((self.n, T, self.H), dtype=torch.int32, device=self.device) if lcd_bits is None else lcd_bits
+    actions = torch.empty((self.n, T, self.A), **f32) if actions is None else actions
+    _lib.check(self.l.blcd_rollout(self.h, T, _ptr(full_state), _ptr(lcd_bits), _ptr(actions), self._stream()))
+    return {'full_state': full_state, 'lcd_bits': lcd_bits, 'action': actions}
+
+  def render_poses_dev(self, poses, variants=None, width=0, height=0):
+    """poses [n, B, 4] float32 (x, y, sin, cos) -> packed frames [n, H] int32"""
+    n = poses.shape[0]
+    out = torch.empty((n, height or self.H), dtype=torch.int32, device=self.device)
+    _lib.check(self.l.blcd_render_poses_sized(self.h, _ptr(poses), _ptr(variants), n, width, height, _ptr(out), self._stream()))
+    return out
+
+  def set_bodies(self, bodies, variants=None):
+    b = torch.as_tensor(np.ascontiguousarray(bodies, np.float32)).to(self.device)
+    v = None if variants is None else torch.as_tensor(np.ascontiguousarray(variants, np.uint32).view(np.int32)).to(self.device)
+    assert tuple(b.shape) == (self.n, self.B, 6)
+    _lib.check(self.l.blcd_set_bodies(self.h, _ptr(b), _ptr(v), self._stream()))
+
+  def get_bodies(self):
+    out = torch.empty((self.n, self.B, 6), dtype=torch.float32, device=self.device)
+    _lib.check(self.l.blcd_get_bodies(self.h, _ptr(out), self._stream()))
+    return out.cpu().numpy()
+
+  def counters(self):
+    out = torch.empty((self.n, 8), dtype=torch.int32, device=self.device)
+    _lib.check(self.l.blcd_get_counters(self.h, _ptr(out), self._stream()))
+    return out.cpu().numpy().view(np.uint32)
+
+  def save_state(self):
+    buf = torch.empty((int(self.l.blcd_state_bytes(self.h)),), dtype=torch.uint8, device=self.device)
+    _lib.check(self.l.blcd_save_state(self.h, _ptr(buf), self._stream()))
+    return buf
+
+  def load_state(self, buf):
+    assert buf.numel() == int(self.l.blcd_state_bytes(self.h))
+    _lib.check(self.l.blcd_load_state(self.h, _ptr(buf), self._stream()))
+
+  def enable_timing(self, on=True):
+    _lib.check(self.l.blcd_enable_timing(self.h, int(on)))
+
+  def last_step_ms(self):
+    ms = C.c_float()
+    _lib.check(self.l.blcd_last_step_ms(self.h, C.byref(ms)))
+    return ms.value
+
+  # -- numpy API with the reference vector-env call shape ----------------------------------------------------------------
+  def unpack_lcd(self, bits, width=None):
+    """packed rows -> bool [..., H, W] (True = background), the reference's `lcd` observation"""
+    w = width or self.W
+    shifts = torch.arange(w, device=bits.device, dtype=torch.int32)
+    return ((bits.unsqueeze(-1) >> shifts) & 1).to(torch.bool)
+
+  def _obs_numpy(self, obs):
+    return {'full_state': obs['full_state'].cpu().numpy(), 'proprio': obs['proprio'].cpu().numpy(),
+            'lcd': self.unpack_lcd(obs['lcd_bits']).cpu().numpy()}
+
+  def reset(self, idxs=None, full_state=None, proprio=None):
+    if proprio is not None:
+      proprio = np.asarray(proprio, np.float32)
+      full_state = np.zeros(proprio.shape[:-1] + (self.S,), np.float32)
+      full_state[..., self.env.pobs_idxs] = proprio
+    idx_t = None if idxs is None else torch.as_tensor(np.asarray(idxs, np.int64)).to(self.device)
+    fs_t = None if full_state is None else torch.as_tensor(np.ascontiguousarray(full_state, np.float32)).to(self.device)
+    self.reset_dev(idx_t, fs_t)
+    obs = self._obs_numpy(self.observe_dev())
+    if idxs is not None:
+      sel = np.asarray(idxs, np.int64)
+      obs = {k: v[sel] for k, v in obs.items()}
+    return obs
+
+  def observe(self):
+    return self._obs_numpy(self.observe_dev())
+
+  def step(self, actions):
+    a = torch.as_tensor(np.ascontiguousarray(actions, np.float32).reshape(self.n, self.A)).to(self.device)
+    obs, _ = self.step_dev(a, observe=True)
+    done = obs['done'].cpu().numpy().astype(bool)
+    return self._obs_numpy(obs), np.zeros(self.n), done, [{'timeout': bool(d)} for d in done]
+
+  def render(self, width=None, height=None):
+    """lcd_render(width, height) for every world from its current pose -> bool [N, height, width]"""
+    width = width or self.W
+    height = height or self.H
+    if (width, height) == (self.W, self.H):
+      return self.unpack_lcd(self.observe_dev()['lcd_bits']).cpu().numpy()
+    if any(self.spec.bodies[b].n_variants > 1 for b in range(self.B)):
+      raise NotImplementedError('resized frames of scenes with shape="random" objects are not built yet')
+    if width > 32:
+      raise NotImplementedError('frames wider than 32 px need the tiled rasterizer path (not built)')
+    b = torch.as_tensor(self.get_bodies()).to(self.device)
+    poses = torch.stack([b[..., 0], b[..., 1], torch.sin(b[..., 2].double()).float(), torch.cos(b[..., 2].double()).float()], -1).contiguous()
+    variants = None
+    bits = self.render_poses_dev(poses, variants, width, height)
+    return self.unpack_lcd(bits, width).cpu().numpy()

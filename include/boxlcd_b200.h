@@ -135,6 +135,11 @@ int blcd_step(blcd_handle h, const float* actions_dev, float* actions_out_dev, u
 int blcd_observe(blcd_handle h, float* full_state_dev, float* proprio_dev, uint32_t* lcd_bits_dev, uint8_t* lcd_bool_dev,
                  uint8_t* done_dev, uint64_t stream);
 
+/* blcd_step immediately followed by blcd_observe in the same kernel (one launch, state stays on chip in between);
+ * this is what WorldEnv.step returns (world_env.py:458).  Any output pointer may be NULL. */
+int blcd_step_observe(blcd_handle h, const float* actions_dev, float* actions_out_dev, float* full_state_dev, float* proprio_dev,
+                      uint32_t* lcd_bits_dev, uint8_t* lcd_bool_dev, uint8_t* done_dev, uint64_t stream);
+
 /* collect.py's inner loop, device resident: for t in [0,T): record obs_t (full_state, lcd bits), draw a_t on device,
  * record it, step.  Outputs are [N, T, ...] (world-major, the npz layout).  Worlds must have been reset by the caller. */
 int blcd_rollout(blcd_handle h, int32_t T, float* full_state_dev, uint32_t* lcd_bits_dev, float* actions_dev, uint64_t stream);
@@ -146,6 +151,10 @@ int blcd_step_host(blcd_handle h, const float* actions_host, float* full_state_h
 /* lcd_render() from explicit poses, no simulation state involved: poses_dev [N, n_bodies, 4] = (x, y, sin, cos) float32
  * of every dynamic body's b2Transform; variant_dev optional [N] uint32 bitmask selecting shape variant per body. */
 int blcd_render_poses(blcd_handle h, const float* poses_dev, const uint32_t* variant_dev, int64_t n, uint32_t* lcd_bits_dev, uint64_t stream);
+
+/* Same at an explicit frame size, lcd_render(width, height) (world_env.py:460-470); 0 = the scene's own size; lcd_w <= 32. */
+int blcd_render_poses_sized(blcd_handle h, const float* poses_dev, const uint32_t* variant_dev, int64_t n, int32_t lcd_w, int32_t lcd_h,
+                            uint32_t* lcd_bits_dev, uint64_t stream);
 
 /* Raw body state, [N, n_bodies, BLCD_BODY_STATE] float32.  blcd_set_bodies puts every world into the state of a freshly
  * built b2World with bodies at those poses/velocities (no contacts yet, zero warm-start impulses, ep_t = 0), which is
@@ -169,6 +178,9 @@ int blcd_enable_timing(blcd_handle h, int on);
 enum { BLCD_CNT_CONTACTS = 0, BLCD_CNT_POS_ITERS = 1, BLCD_CNT_TOI_EVENTS = 2, BLCD_CNT_TOI_CALLS = 3, BLCD_CNT_SLEEP_STEPS = 4,
        BLCD_CNT_OVERFLOW = 5, BLCD_CNT_MANIFOLD_POINTS = 6, BLCD_CNT_SUBSTEPS = 7 };
 int blcd_get_counters(blcd_handle h, uint32_t* counters_dev, uint64_t stream);
+/* out16: n_bodies, n_joints, n_walls, n_pairs, obs_size, pobs_size, act_size, lcd_w, lcd_h, manifold slots per world,
+ * state words per world, shared-memory words per world, threads per block, shared-memory bytes per block, 0, 0 */
+int blcd_scene_info(blcd_handle h, int32_t* out16);
 
 #ifdef __cplusplus
 }

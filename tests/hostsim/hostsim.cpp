@@ -1,0 +1,145 @@
+// hostsim.cpp -- TEST TOOL: compiles the CUDA path's per-world simulation source (boxlcd_b200/csrc/blcd_world.cuh)
+// for the host, so its logic can be compared bit-for-bit with the CPU oracle in a container that has no GPU.
+// It is never loaded by the product; the product path is libboxlcd_b200.so on a GPU and nothing else.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "blcd_world.cuh"
+
+using namespace blcd;
+
+struct HostSim {
+  DScene scene;
+  std::vector<uint32_t> state;
+  std::vector<float> hot;
+  int64_t n, offset;
+  uint64_t seed;
+};
+
+extern "C" {
+
+void* hostsim_new(const blcd_spec* spec, int64_t n, uint64_t seed, int64_t offset, int maxm) {
+  HostSim* h = new HostSim();
+  if (maxm <= 0) maxm = spec->n_bodies <= 2 ? 4 : (spec->n_bodies <= 4 ? 6 : (spec->n_bodies == 5 ? 8 : 16));  // same default as blcd_create
+  if (host::build_scene(h->scene, *spec, maxm)) { delete h; return nullptr; }
+  h->n = n; h->seed = seed; h->offset = offset;
+  h->state.assign((size_t)h->scene.state_words * n, 0u);
+  h->hot.assign((size_t)h->scene.hot_words, 0.0f);
+  for (int64_t w = 0; w < n; ++w)
+    for (int s = 0; s < h->scene.maxm; ++s) h->state[(size_t)(h->scene.off_slots + kSlotWords * s) * n + w] = kSlotFree;
+  return h;
+}
+void hostsim_free(void* p) { delete (HostSim*)p; }
+
+#define SIM(w) Sim<1> sim(h->scene, h->hot.data(), h->state.data(), h->n, (w)); sim.load(h->seed, h->offset + (w))
+
+void hostsim_reset(void* p, const float* full_state) {
+  HostSim* h = (HostSim*)p;
+  for (int64_t w = 0; w < h->n; ++w) {
+    SIM(w);
+    sim.reset(full_state ? full_state + w * h->scene.S : nullptr);
+    sim.store();
+  }
+}
+
+void hostsim_set_bodies(void* p, const float* bodies, const uint32_t* variants) {
+  HostSim* h = (HostSim*)p;
+  const DScene& sc = h->scene;
+  for (int64_t w = 0; w < h->n; ++w) {
+    SIM(w);
+    sim.variant = variants ? (variants[w] & 0xFFu) : 0u;
+    float pose[BLCD_MAX_BODIES][3];
+    const float* src = bodies + w * sc.nb * BLCD_BODY_STATE;
+    for (int b = 0; b < sc.nb; ++b) { pose[b][0] = src[b * 6]; pose[b][1] = src[b * 6 + 1]; pose[b][2] = src[b * 6 + 2]; }
+    sim.build_fresh(pose);
+    for (int b = 0; b < sc.nb; ++b) { sim.v[b] = mk(src[b * 6 + 3], src[b * 6 + 4]); sim.w[b] = src[b * 6 + 5]; }
+    sim.store();
+  }
+}
+
+void hostsim_get_bodies(void* p, float* bodies) {
+  HostSim* h = (HostSim*)p;
+  const DScene& sc = h->scene;
+  for (int64_t w = 0; w < h->n; ++w) {
+    SIM(w);
+    for (int b = 0; b < sc.nb; ++b) {
+      float* d = bodies + (w * sc.nb + b) * BLCD_BODY_STATE;
+      d[0] = sim.xf[b].p.x; d[1] = sim.xf[b].p.y; d[2] = sim.a[b]; d[3] = sim.v[b].x; d[4] = sim.v[b].y; d[5] = sim.w[b];
+    }
+  }
+}
+
+static void write_obs(const Sim<1>& sim, const DScene& sc, float* fs_out, uint32_t* bits_out) {
+  if (fs_out)
+    for (int b = 0; b < sc.nb; ++b) {
+      float ob[4];
+      sim.obs_body(b, ob);
+      for (int k = 0; k < 4; ++k) fs_out[sc.body[b].obs[k]] = ob[k];
+    }
+  if (bits_out)
+    for (int R = 0; R < sc.lcd_h; ++R) bits_out[R] = sim.lcd_row(R);
+}
+
+void hostsim_step(void* p, const float* actions, float* actions_out) {
+  HostSim* h = (HostSim*)p;
+  const DScene& sc = h->scene;
+  for (int64_t w = 0; w < h->n; ++w) {
+    SIM(w);
+    float act[BLCD_MAX_OBS];
+    if (actions) memcpy(act, actions + w * sc.A, sizeof(float) * sc.A);
+    else sim.draw_action(act);
+    if (actions_out) memcpy(actions_out + w * sc.A, act, sizeof(float) * sc.A);
+    sim.env_step(act);
+    sim.store();
+  }
+}
+
+void hostsim_observe(void* p, float* full_state, uint32_t* bits) {
+  HostSim* h = (HostSim*)p;
+  const DScene& sc = h->scene;
+  for (int64_t w = 0; w < h->n; ++w) {
+    SIM(w);
+    write_obs(sim, sc, full_state ? full_state + w * sc.S : nullptr, bits ? bits + w * sc.lcd_h : nullptr);
+  }
+}
+
+void hostsim_rollout(void* p, int T, float* full_state, uint32_t* bits, float* actions) {
+  HostSim* h = (HostSim*)p;
+  const DScene& sc = h->scene;
+  for (int64_t w = 0; w < h->n; ++w) {
+    SIM(w);
+    float act[BLCD_MAX_OBS];
+    for (int t = 0; t < T; ++t) {
+      int64_t row = w * T + t;
+      write_obs(sim, sc, full_state ? full_state + row * sc.S : nullptr, bits ? bits + row * sc.lcd_h : nullptr);
+      sim.draw_action(act);
+      if (actions) memcpy(actions + row * sc.A, act, sizeof(float) * sc.A);
+      sim.env_step(act);
+    }
+    sim.store();
+  }
+}
+
+void hostsim_counters(void* p, uint32_t* out) {
+  HostSim* h = (HostSim*)p;
+  for (int64_t w = 0; w < h->n; ++w)
+    for (int k = 0; k < BLCD_N_COUNTERS; ++k) out[w * BLCD_N_COUNTERS + k] = h->state[(size_t)(h->scene.off_cnt + k) * h->n + w];
+}
+
+void hostsim_render_poses(void* p, const float* poses, const uint32_t* variants, int64_t n, int lcd_w, int lcd_h, uint32_t* bits) {
+  HostSim* h = (HostSim*)p;
+  const DScene& sc = h->scene;
+  if (lcd_w <= 0) lcd_w = sc.lcd_w;
+  if (lcd_h <= 0) lcd_h = sc.lcd_h;
+  for (int64_t w = 0; w < n; ++w)
+    for (int R = 0; R < lcd_h; ++R) {
+      uint32_t ink = 0u, variant = variants ? variants[w] : 0u;
+      for (int b = 0; b < sc.nb; ++b) {
+        const float* q = poses + (w * sc.nb + b) * 4;
+        ink |= body_row(sc.body[b].shape[(variant >> b) & 1u], q[0], q[1], q[2], q[3], lcd_h - 1 - R, sc.world_w, lcd_w, lcd_h, sc.rules);
+      }
+      bits[w * lcd_h + R] = row_bits_from_ink(ink, lcd_w);
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+"""ctypes wrapper of tests/hostsim (the CUDA path's simulation source compiled for the host; TEST TOOL ONLY)."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'hostsim')
+LIB = os.path.join(HERE, '_build', 'libhostsim.so')
+_lib = None
+
+
+def lib():
+  global _lib
+  if _lib is None:
+    subprocess.run(['make', '-s', '-C', HERE], check=True)
+    l = C.CDLL(LIB)
+    vp, i64 = C.c_void_p, C.c_int64
+    l.hostsim_new.argtypes = [vp, i64, C.c_uint64, i64, C.c_int]
+    l.hostsim_new.restype = vp
+    l.hostsim_free.argtypes = [vp]
+    l.hostsim_reset.argtypes = [vp, vp]
+    l.hostsim_set_bodies.argtypes = [vp, vp, vp]
+    l.hostsim_get_bodies.argtypes = [vp, vp]
+    l.hostsim_step.argtypes = [vp, vp, vp]
+    l.hostsim_observe.argtypes = [vp, vp, vp]
+    l.hostsim_rollout.argtypes = [vp, C.c_int, vp, vp, vp]
+    l.hostsim_counters.argtypes = [vp, vp]
+    l.hostsim_render_poses.argtypes = [vp, vp, vp, i64, C.c_int, C.c_int, vp]
+    _lib = l
+  return _lib
+
+
+def _p(a):
+  return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class HostSim:
+  def __init__(self, spec, n, seed=0, world_offset=0, maxm=0):
+    self.l = lib()
+    self.spec, self.n = spec, int(n)
+    self.h = self.l.hostsim_new(C.byref(spec), self.n, seed, world_offset, maxm)
+    assert self.h, 'scene rejected'
+    self.B, self.S, self.A, self.H, self.W = spec.n_bodies, spec.obs_size, spec.act_size, spec.lcd_h, spec.lcd_w
+
+  def __del__(self):
+    if getattr(self, 'h', None):
+      self.l.hostsim_free(self.h)
+      self.h = None
+
+  def reset(self, full_state=None):
+    fs = None if full_state is None else np.ascontiguousarray(full_state, np.float32)
+    self.l.hostsim_reset(self.h, _p(fs))
+
+  def set_bodies(self, bodies, variants=None):
+    b = np.ascontiguousarray(bodies, np.float32)
+    v = None if variants is None else np.ascontiguousarray(variants, np.uint32)
+    self.l.hostsim_set_bodies(self.h, _p(b), _p(v))
+
+  def get_bodies(self):
+    out = np.zeros((self.n, self.B, 6), np.float32)
+    self.l.hostsim_get_bodies(self.h, _p(out))
+    return out
+
+  def step(self, actions=None):
+    a = None if actions is None else np.ascontiguousarray(actions, np.float32)
+    out = np.zeros((self.n, self.A), np.float32)
+    self.l.hostsim_step(self.h, _p(a), _p(out))
+    return out
+
+  def observe(self):
+    fs = np.zeros((self.n, self.S), np.float32)
+    bits = np.zeros((self.n, self.H), np.uint32)
+    self.l.hostsim_observe(self.h, _p(fs), _p(bits))
+    return {'full_state': fs, 'lcd_bits': bits}
+
+  def rollout(self, T):
+    fs = np.zeros((self.n, T, self.S), np.float32)
+    bits = np.zeros((self.n, T, self.H), np.uint32)
+    act = np.zeros((self.n, T, self.A), np.float32)
+    self.l.hostsim_rollout(self.h, T, _p(fs), _p(bits), _p(act))
+    return {'full_state': fs, 'lcd_bits': bits, 'action': act}
+
+  def counters(self):
+    out = np.zeros((self.n, 8), np.uint32)
+    self.l.hostsim_counters(self.h, _p(out))
+    return out
+
+  def render_poses(self, poses, variants=None, lcd_w=0, lcd_h=0):
+    poses = np.ascontiguousarray(poses, np.float32)
+    n = poses.shape[0]
+    v = None if variants is None else np.ascontiguousarray(variants, np.uint32)
+    bits = np.zeros((n, lcd_h or self.H), np.uint32)
+    self.l.hostsim_render_poses(self.h, _p(poses), _p(v), n, lcd_w, lcd_h, _p(bits))
+    return bits

@@ -1,0 +1,195 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libboxlcd_b200.so via boxlcd_b200.vec_env), against the
+CPU oracle on the same seeded inputs and against the committed reference frames.
+
+Bars (BASELINE.json north_star): LCD frames from identical poses BIT-EXACT; single-step body states within 1e-4
+relative on position and angle (we also check 1e-5 absolute on almost every world); long rollouts statistically."""
+import os
+import numpy as np
+import pytest
+import torch
+import boxlcd_b200 as blcd
+from oracle import oracle
+from common import make_env, random_bodies, rel_err, ENVS_CORE
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden', 'lcd_golden.npz')
+
+
+def vec(env, n, **kw):
+  from boxlcd_b200.vec_env import VecWorldEnv
+  return VecWorldEnv(env, n, **kw)
+
+
+def i32(a):
+  return np.ascontiguousarray(a).view(np.int32)
+
+
+@pytest.mark.parametrize('name', ['Dropbox', 'Bounce2', 'Object2', 'Urchin', 'Luxo', 'UrchinCube', 'LuxoCube', 'UrchinBall', 'LuxoBall'])
+def test_frames_bit_exact_vs_reference_golden(name):
+  gold = np.load(GOLD)
+  env = make_env(name)
+  v = vec(env, 1)
+  kind = gold[f'{name}_kind']
+  poses = torch.as_tensor(gold[f'{name}_poses']).cuda()
+  variants = None
+  if any(env.layout.spec.bodies[b].n_variants > 1 for b in range(kind.shape[1])):
+    variants = torch.as_tensor(i32(((kind != 0).astype(np.uint32) * (1 << np.arange(kind.shape[1])).astype(np.uint32)).sum(1).astype(np.uint32))).cuda()
+  bits = v.render_poses_dev(poses, variants).cpu().numpy().view(np.uint32)
+  assert (bits == gold[f'{name}_bits']).all()
+
+
+@pytest.mark.parametrize('name', ['Urchin', 'UrchinBall', 'LuxoCube'])
+def test_frames_bit_exact_vs_oracle_many_poses(name):
+  env = make_env(name)
+  sp = env.layout.spec
+  n = 200_000
+  rng = np.random.RandomState(0)
+  ow = oracle.OracleWorlds(sp, 1)
+  ow.reset()
+  shapes = ow.lcd_shapes(0)
+  poses = np.zeros((n, sp.n_bodies, 4), np.float32)
+  poses[..., 0] = rng.uniform(-0.2, env.WIDTH + 0.2, poses.shape[:2])
+  poses[..., 1] = rng.uniform(-0.2, env.HEIGHT + 0.2, poses.shape[:2])
+  ang = rng.uniform(-np.pi, np.pi, poses.shape[:2]).astype(np.float32)
+  ang[rng.uniform(size=ang.shape) < 0.3] = 0.0
+  poses[..., 2], poses[..., 3] = np.sin(ang.astype(np.float64)), np.cos(ang.astype(np.float64))
+  ref = oracle.lcd_render(shapes, poses, env.WIDTH, sp.lcd_w, sp.lcd_h)
+  v = vec(env, 1)
+  bits = v.render_poses_dev(torch.as_tensor(poses).cuda()).cpu().numpy().view(np.uint32)
+  assert (bits == ref).all(), f'{(bits != ref).any(1).sum()} / {n} frames differ'
+
+
+def test_render_at_other_sizes_matches_oracle():
+  env = make_env('Urchin')
+  sp = env.layout.spec
+  ow = oracle.OracleWorlds(sp, 64, seed=4)
+  ow.reset()
+  poses, _ = ow.get_poses()
+  v = vec(env, 1)
+  for (w, h) in [(32, 16), (16, 8), (24, 12), (32, 32)]:
+    ref = oracle.lcd_render(ow.lcd_shapes(0), poses, env.WIDTH, w, h)
+    bits = v.render_poses_dev(torch.as_tensor(poses).cuda(), None, w, h).cpu().numpy().view(np.uint32)
+    assert (bits == ref).all(), (w, h)
+
+
+@pytest.mark.parametrize('name', ENVS_CORE)
+def test_reset_matches_oracle(name):
+  env = make_env(name)
+  n = 2048
+  ow = oracle.OracleWorlds(env.layout.spec, n, seed=7, threads=8)
+  ow.reset()
+  v = vec(env, n, seed=7)
+  v.reset_dev()
+  b_gpu, b_cpu = v.get_bodies(), ow.get_bodies()
+  assert np.abs(b_gpu - b_cpu).max() < 2e-6   # fp64 atan2 / sincos may differ in the last bit between libm and CUDA
+  o_gpu, o_cpu = v.observe(), ow.observe()
+  assert np.abs(o_gpu['full_state'] - o_cpu['full_state']).max() < 2e-6
+  same = (oracle.unpack_bits(o_cpu['lcd_bits'], v.W) == o_gpu['lcd']).all((1, 2)).mean()
+  assert same > 0.999   # a last-bit pose difference can move a vertex across a pixel boundary
+
+
+@pytest.mark.parametrize('name', ENVS_CORE)
+def test_single_env_step_within_tolerance_of_oracle(name):
+  """north_star: single-step body states from identical states within 1e-4 relative on position and angle"""
+  env = make_env(name)
+  rng = np.random.RandomState(3)
+  n = 4096
+  bodies, variants = random_bodies(env, n, rng)
+  act = rng.uniform(-1.2, 1.2, (n, env.act_size)).astype(np.float32)
+  ow = oracle.OracleWorlds(env.layout.spec, n, threads=8)
+  ow.set_bodies(bodies, variants)
+  ow.step(act)
+  ref = ow.get_bodies()
+  v = vec(env, n)
+  v.set_bodies(bodies, variants)
+  v.step_dev(torch.as_tensor(act).cuda(), observe=False)
+  out = v.get_bodies()
+  assert v.counters()[:, 5].sum() == 0, 'manifold slots overflowed'
+  pos_err = np.abs(out[..., :3] - ref[..., :3]).max((1, 2))
+  rel = rel_err(out[..., :3], ref[..., :3]).max((1, 2))
+  frac_1e5 = (pos_err < 1e-5).mean()
+  frac_rel = (rel < 1e-4).mean()
+  print(f'{name}: max abs err median {np.median(pos_err):.2e}, <1e-5 abs: {frac_1e5:.4f}, <1e-4 rel: {frac_rel:.4f}, worst {pos_err.max():.2e}')
+  # a contact decision that flips on a last-bit difference (sincosf vs libm) is a different but equally valid solve;
+  # everything else must agree to round-off
+  assert frac_rel > 0.995
+  assert frac_1e5 > 0.98
+  vel_rel = rel_err(out[..., 3:], ref[..., 3:]).max((1, 2))
+  assert (vel_rel < 1e-3).mean() > 0.99
+
+
+@pytest.mark.parametrize('name', ['Urchin', 'Bounce2', 'LuxoCube'])
+def test_rollout_matches_oracle_early_and_statistically(name):
+  env = make_env(name)
+  sp = env.layout.spec
+  n, T = 2048, 30
+  ow = oracle.OracleWorlds(sp, n, seed=5, threads=8)
+  ow.reset()
+  ro = ow.rollout(T, want=('full_state', 'lcd_bits', 'action'))
+  v = vec(env, n, seed=5)
+  v.reset_dev()
+  rg = v.rollout_dev(T)
+  fs, bits, act = rg['full_state'].cpu().numpy(), rg['lcd_bits'].cpu().numpy().view(np.uint32), rg['action'].cpu().numpy()
+  assert (act == ro['action']).all(), 'device Philox stream must equal the oracle stream'
+  # step 1 (one env step after reset) agrees to round-off on nearly every world
+  assert (np.abs(fs[:, 1] - ro['full_state'][:, 1]).max(1) < 1e-5).mean() > 0.98
+  # later steps: chaotic divergence allowed, distributions must agree
+  ink_g = (~oracle.unpack_bits(bits, sp.lcd_w)).sum((2, 3)).mean(0)
+  ink_c = (~oracle.unpack_bits(ro['lcd_bits'], sp.lcd_w)).sum((2, 3)).mean(0)
+  assert np.abs(ink_g - ink_c).max() < 0.05 * ink_c.mean() + 0.3
+  for k in range(fs.shape[2]):
+    assert abs(fs[:, -1, k].mean() - ro['full_state'][:, -1, k].mean()) < 0.06, k
+  assert v.counters()[:, 5].sum() == 0
+
+
+def test_step_observe_and_vector_env_call_shape():
+  env = make_env('UrchinBall')
+  n = 256
+  v = vec(env, n, seed=1)
+  obs = v.reset()
+  assert obs['full_state'].shape == (n, 20) and obs['proprio'].shape == (n, 16) and obs['lcd'].shape == (n, 16, 24) and obs['lcd'].dtype == bool
+  a = np.stack([env.action_space.sample() for _ in range(n)])
+  obs2, rew, done, infos = v.step(a)
+  assert rew.shape == (n,) and done.shape == (n,) and not done.any() and infos[0] == {'timeout': False}
+  assert (obs2['proprio'] == obs2['full_state'][:, env.pobs_idxs]).all()
+  # reset(idxs, proprio=...) renders the given robot state (research/wrappers/async_vector_env.py:147-155)
+  sub = v.reset(idxs=[3, 5], proprio=obs['proprio'][[3, 5]])
+  assert np.abs(sub['proprio'] - obs['proprio'][[3, 5]]).max() < 2e-6
+  # done after ep_len steps
+  env2 = make_env('Dropbox', ep_len=3)
+  v2 = vec(env2, 4)
+  v2.reset()
+  for t in range(3):
+    _, _, done, infos = v2.step(np.zeros((4, 1), np.float32))
+  assert done.all() and infos[0]['timeout']
+
+
+def test_single_env_api_is_a_drop_in():
+  env = blcd.envs.Urchin()
+  env.seed(0)
+  obs = env.reset()
+  assert set(obs) == {'full_state', 'proprio', 'lcd'} and obs['lcd'].shape == (16, 32) and obs['full_state'].dtype == np.float64
+  for _ in range(5):
+    obs, rew, done, info = env.step(env.action_space.sample())
+  assert rew == 0.0 and done is False and info == {'timeout': False}
+  lcd = env.lcd_render()
+  assert (lcd == obs['lcd']).all()
+  again = env.reset(full_state=obs['full_state'])
+  assert np.abs(again['full_state'] - obs['full_state']).max() < 2e-6
+  env.close()
+
+
+def test_state_save_load_round_trip_and_sharding_invariance():
+  env = make_env('Urchin')
+  v = vec(env, 512, seed=9)
+  v.reset_dev()
+  v.rollout_dev(5)
+  snap = v.save_state()
+  a = v.rollout_dev(10)['full_state'].clone()
+  v.load_state(snap)
+  b = v.rollout_dev(10)['full_state']
+  assert torch.equal(a, b)
+  # worlds keyed by global index: a shard starting at offset 256 reproduces worlds 256.. of the full batch
+  full = vec(env, 512, seed=9); full.reset_dev(); f = full.rollout_dev(8)['full_state']
+  half = vec(env, 256, seed=9, world_offset=256); half.reset_dev(); h = half.rollout_dev(8)['full_state']
+  assert torch.equal(f[256:], h)
