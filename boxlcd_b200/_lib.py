@@ -5,7 +5,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libboxlcd_b200.so')
+LIB_PATH = os.environ.get('BLCD_LIB') or os.path.join(HERE, 'libboxlcd_b200.so')   # BLCD_LIB: experiment builds only
 CSRC = os.path.join(HERE, 'csrc')
 _lib = None
 

@@ -19,11 +19,25 @@
 
 namespace blcd {
 
+constexpr int kSceneBytes = (int)((sizeof(DScene) + 15) / 16 * 16);
+
+#ifdef __CUDACC__
+// dynamic shared memory of every simulation kernel: [DScene copy][hot words x block threads].  Going through this
+// symbol (instead of a pointer stored in the Sim object) lets the compiler emit LDS/STS and know that these stores
+// cannot alias the thread's local state.
+extern __shared__ __align__(16) unsigned char blcd_smem[];
+#endif
+
 template <int STRIDE>
 struct Hot {
   float* p;
-  BLCD_HD float& operator[](int i) const { return p[i * STRIDE]; }
-  BLCD_HD uint32_t& u(int i) const { return reinterpret_cast<uint32_t*>(p)[i * STRIDE]; }
+#ifdef __CUDA_ARCH__
+  BLCD_HD float* base() const { return reinterpret_cast<float*>(blcd_smem + kSceneBytes) + threadIdx.x; }
+#else
+  BLCD_HD float* base() const { return p; }
+#endif
+  BLCD_HD float& operator[](int i) const { return base()[i * STRIDE]; }
+  BLCD_HD uint32_t& u(int i) const { return reinterpret_cast<uint32_t*>(base())[i * STRIDE]; }
 };
 
 struct Gw {  // view of one world's persistent words in HBM
@@ -78,10 +92,27 @@ enum { P_RAX = 0, P_RAY, P_RBX, P_RBY, P_NM, P_TM, P_BIAS, P_NI, P_TI };
 enum { S_HDR = 0, S_LNX, S_LNY, S_LPX, S_LPY, S_PT };  // point j at S_PT + 5 j: x, y, ni, ti, id
 constexpr uint32_t kSlotFree = 0xFFFFFFFFu;
 
+// Velocity-constraint record of one joint held in REGISTERS for the whole velocity loop (solve order k is a
+// compile-time index after unrolling; only the body rows it touches are runtime values).  Everything that
+// b2RevoluteJoint::SolveVelocityConstraints recomputes identically every iteration (cross(ey, ez), the 3x3 and 2x2
+// determinants) is hoisted: same operations on the same inputs, so the results are bit-identical.
+struct JV {
+  int rowA, rowB, limitState, flags;  // flags: 1 = motor enabled, 2 = limit enabled, 4 = fixed rotation
+  float rAx, rAy, rBx, rBy, exx, eyx, ezx, eyy, ezy, ezz;
+  float cx, cy, cz, det3, det2, mm, maxImp, ms, mA, iA, mB, iB;
+  float ix, iy, iz, mi;
+};
+
 template <int STRIDE>
 struct Sim {
-  const DScene& sc;
+  const DScene* scene_host;
   Hot<STRIDE> hot;
+#ifdef __CUDA_ARCH__
+  BLCD_HD const DScene& scene() const { return *reinterpret_cast<const DScene*>(blcd_smem); }
+#else
+  BLCD_HD const DScene& scene() const { return *scene_host; }
+#endif
+#define sc scene()
   Gw g;
   // body state (registers / local memory)
   V2 c[BLCD_MAX_BODIES], c0[BLCD_MAX_BODIES], v[BLCD_MAX_BODIES];
@@ -104,7 +135,7 @@ struct Sim {
   int8_t islandOf[BLCD_MAX_BODIES];
   int nIslands, nc, njo;
 
-  BLCD_HD Sim(const DScene& s, float* hot_base, uint32_t* state, int64_t n_worlds, int64_t world) : sc(s) {
+  BLCD_HD Sim(const DScene& s, float* hot_base, uint32_t* state, int64_t n_worlds, int64_t world) : scene_host(&s) {
     hot.p = hot_base;
     g.p = state + world;
     g.n = n_worlds;
@@ -489,7 +520,8 @@ struct Sim {
     set_hv(rB_, vB, wB);
   }
 
-  BLCD_HD void contact_solve_velocity(int k) {
+  // returns true if any impulse applied by this sweep was non-zero
+  BLCD_HD bool contact_solve_velocity(int k) {
     const int h = sc.h_con + kHotCon * k;
     uint32_t pk = hot.u(h + C_PK);
     int rA_ = pk & 15u, rB_ = (pk >> 4) & 15u, count = (pk >> 8) & 15u;
@@ -499,6 +531,7 @@ struct Sim {
     V2 normal = mk(hot[h + C_NX], hot[h + C_NY]);
     V2 tangent = cross(normal, 1.0f);
     float friction = hot[h + C_FR];
+    bool changed = false;
     for (int j = 0; j < 2; ++j) {
       if (j < count) {
         int q = h + C_PT + kHotConPt * j;
@@ -510,6 +543,7 @@ struct Sim {
         float oldImpulse = hot[q + P_TI];
         float newImpulse = clampb(oldImpulse + lambda, -maxFriction, maxFriction);
         lambda = newImpulse - oldImpulse;
+        changed |= (lambda != 0.0f);
         hot[q + P_TI] = newImpulse;
         V2 P = lambda * tangent;
         vA -= mA * P;
@@ -527,6 +561,7 @@ struct Sim {
       float oldImpulse = hot[q + P_NI];
       float newImpulse = fmaxb(oldImpulse + lambda, 0.0f);
       lambda = newImpulse - oldImpulse;
+      changed |= (lambda != 0.0f);
       hot[q + P_NI] = newImpulse;
       V2 P = lambda * normal;
       vA -= mA * P;
@@ -564,6 +599,7 @@ struct Sim {
       }
       if (found) {
         V2 d = x - aa;
+        changed |= (d.x != 0.0f) | (d.y != 0.0f);
         V2 P1 = d.x * normal, P2 = d.y * normal;
         vA -= mA * (P1 + P2);
         wA -= iA * (cross(r1A, P1) + cross(r2A, P2));
@@ -575,6 +611,7 @@ struct Sim {
     }
     set_hv(rA_, vA, wA);
     set_hv(rB_, vB, wB);
+    return changed;
   }
 
   BLCD_HD void contact_store_impulses(int k) {
@@ -784,6 +821,88 @@ struct Sim {
     set_hv(rB_, vB, wB);
   }
 
+  BLCD_HD void jv_load(JV& q, int j, float h_dt) const {
+    const DJoint& jd = sc.joint[j];
+    const int h = sc.h_joint + kHotJoint * j;
+    q.rowA = jd.a; q.rowB = jd.b;
+    uint32_t pk = hot.u(h + J_PK);
+    q.limitState = (int)(pk & 3u);
+    q.flags = (jd.enableMotor ? 1 : 0) | (jd.enableLimit ? 2 : 0) | (((pk >> 8) & 1u) ? 4 : 0);
+    q.rAx = hot[h + J_RAX]; q.rAy = hot[h + J_RAY]; q.rBx = hot[h + J_RBX]; q.rBy = hot[h + J_RBY];
+    q.exx = hot[h + J_EXX]; q.eyx = hot[h + J_EYX]; q.ezx = hot[h + J_EZX]; q.eyy = hot[h + J_EYY]; q.ezy = hot[h + J_EZY]; q.ezz = hot[h + J_EZZ];
+    q.cx = q.eyy * q.ezz - q.ezy * q.ezy; q.cy = q.ezy * q.ezx - q.eyx * q.ezz; q.cz = q.eyx * q.ezy - q.eyy * q.ezx;  // cross(ey, ez)
+    float det = q.exx * q.cx + q.eyx * q.cy + q.ezx * q.cz;
+    if (det != 0.0f) det = 1.0f / det;
+    q.det3 = det;
+    float d2 = q.exx * q.eyy - q.eyx * q.eyx;
+    if (d2 != 0.0f) d2 = 1.0f / d2;
+    q.det2 = d2;
+    q.mm = hot[h + J_MM]; q.maxImp = h_dt * jd.maxTorque; q.ms = hot[h + J_MS];
+    q.mA = hm(q.rowA); q.iA = hi(q.rowA); q.mB = hm(q.rowB); q.iB = hi(q.rowB);
+    q.ix = hot[h + J_IX]; q.iy = hot[h + J_IY]; q.iz = hot[h + J_IZ]; q.mi = hot[h + J_MI];
+  }
+
+  BLCD_HD void jv_save(const JV& q, int j) const {
+    const int h = sc.h_joint + kHotJoint * j;
+    hot[h + J_IX] = q.ix; hot[h + J_IY] = q.iy; hot[h + J_IZ] = q.iz; hot[h + J_MI] = q.mi;
+  }
+
+  // b2RevoluteJoint::SolveVelocityConstraints on a register-resident record.  The point-to-point branch is folded into
+  // the limit branch's apply step with iz = 0 (x + 0 == x), so that lanes only diverge over the small solves.
+  BLCD_HD void jv_solve(JV& q) const {
+    V2 vA = hv(q.rowA), vB = hv(q.rowB);
+    float wA = hw(q.rowA), wB = hw(q.rowB);
+    const bool rot = (q.flags & 4) == 0;  // !fixedRotation
+    const V2 rA = mk(q.rAx, q.rAy), rB = mk(q.rBx, q.rBy);
+    if ((q.flags & 1) && q.limitState != 3 && rot) {
+      float Cdot = wB - wA - q.ms;
+      float impulse = -q.mm * Cdot;
+      float oldImpulse = q.mi;
+      q.mi = clampb(oldImpulse + impulse, -q.maxImp, q.maxImp);
+      impulse = q.mi - oldImpulse;
+      wA -= q.iA * impulse;
+      wB += q.iB * impulse;
+    }
+    V2 Cdot1 = vB + cross(wB, rB) - vA - cross(wA, rA);
+    float ix, iy, iz;
+    const bool limited = (q.flags & 2) && q.limitState != 0 && rot;
+    if (limited) {
+      float bx = Cdot1.x, by = Cdot1.y, bz = wB - wA;
+      ix = q.det3 * (bx * q.cx + by * q.cy + bz * q.cz);
+      float ux = by * q.ezz - bz * q.ezy, uy = bz * q.ezx - bx * q.ezz, uz = bx * q.ezy - by * q.ezx;        // cross(b, ez)
+      iy = q.det3 * (q.exx * ux + q.eyx * uy + q.ezx * uz);
+      float tx = q.eyy * bz - q.ezy * by, ty = q.ezy * bx - q.eyx * bz, tz = q.eyx * by - q.eyy * bx;        // cross(ey, b)
+      iz = q.det3 * (q.exx * tx + q.eyx * ty + q.ezx * tz);
+      ix = -ix; iy = -iy; iz = -iz;
+      bool reduce = false;
+      if (q.limitState == 1) reduce = (q.iz + iz) < 0.0f;
+      else if (q.limitState == 2) reduce = (q.iz + iz) > 0.0f;
+      if (reduce) {
+        V2 rhs = -Cdot1 + q.iz * mk(q.ezx, q.ezy);
+        ix = q.det2 * (q.eyy * rhs.x - q.eyx * rhs.y);
+        iy = q.det2 * (q.exx * rhs.y - q.eyx * rhs.x);
+        iz = -q.iz;
+        q.ix += ix; q.iy += iy; q.iz = 0.0f;
+      } else {
+        q.ix += ix; q.iy += iy; q.iz += iz;
+      }
+    } else {
+      V2 nb_ = -Cdot1;
+      ix = q.det2 * (q.eyy * nb_.x - q.eyx * nb_.y);
+      iy = q.det2 * (q.exx * nb_.y - q.eyx * nb_.x);
+      iz = 0.0f;
+      q.ix += ix;
+      q.iy += iy;
+    }
+    V2 P = mk(ix, iy);
+    vA -= q.mA * P;
+    wA -= q.iA * (cross(rA, P) + iz);
+    vB += q.mB * P;
+    wB += q.iB * (cross(rB, P) + iz);
+    set_hv(q.rowA, vA, wA);
+    set_hv(q.rowB, vB, wB);
+  }
+
   BLCD_HD bool joint_solve_position(int j) {
     const DJoint& jd = sc.joint[j];
     const int h = sc.h_joint + kHotJoint * j;
@@ -840,7 +959,7 @@ struct Sim {
   }
 
   // ---- b2World::Solve -------------------------------------------------------------------------------------------------
-  BLCD_HDN void solve(float h_dt, float dtRatio) {
+  BLCD_HD void solve(float h_dt, float dtRatio) {
     const int nb = sc.nb;
     uint8_t corder[32];           // contact record k -> nothing to map: records are filled in solve order
     uint8_t jorder[BLCD_MAX_JOINTS];
@@ -923,9 +1042,31 @@ struct Sim {
     for (int k = 0; k < nc; ++k) contact_warm_start(k);
     for (int k = 0; k < njo; ++k) joint_init(jorder[k], jisl[k], dtRatio, h_dt);
     const int vi = sc.vel_iters;
-    for (int it = 0; it < vi; ++it) {
-      for (int k = 0; k < njo; ++k) joint_solve_velocity(jorder[k], h_dt);
-      for (int k = 0; k < nc; ++k) contact_solve_velocity(k);
+    if (njo <= 3) {
+      // up to three joints (every reference robot in scope) live in registers for the whole loop; contacts, whose
+      // number is data dependent, stay in shared memory
+      JV ja, jb, jc;
+      if (njo > 0) jv_load(ja, jorder[0], h_dt);
+      if (njo > 1) jv_load(jb, jorder[1], h_dt);
+      if (njo > 2) jv_load(jc, jorder[2], h_dt);
+      const int njo_ = njo, nc_ = nc;
+      for (int it = 0; it < vi; ++it) {
+        if (njo_ > 0) jv_solve(ja);
+        if (njo_ > 1) jv_solve(jb);
+        if (njo_ > 2) jv_solve(jc);
+        bool changed = false;
+        for (int k = 0; k < nc_; ++k) changed |= contact_solve_velocity(k);
+        // a sweep that applied no impulse leaves the state untouched, so every later sweep repeats it exactly
+        if (njo_ == 0 && !changed) break;
+      }
+      if (njo > 0) jv_save(ja, jorder[0]);
+      if (njo > 1) jv_save(jb, jorder[1]);
+      if (njo > 2) jv_save(jc, jorder[2]);
+    } else {
+      for (int it = 0; it < vi; ++it) {
+        for (int k = 0; k < njo; ++k) joint_solve_velocity(jorder[k], h_dt);
+        for (int k = 0; k < nc; ++k) contact_solve_velocity(k);
+      }
     }
     for (int k = 0; k < nc; ++k) contact_store_impulses(k);
     // integrate positions
@@ -1125,8 +1266,11 @@ struct Sim {
         uint32_t pk = hot.u(sc.h_con + kHotCon * k + C_PK);
         contact_init(k, (int)((pk >> 12) & 255u), 0, 1.0f, false);
       }
-      for (int it = 0; it < sc.vel_iters; ++it)
-        for (int k = 0; k < ntc; ++k) contact_solve_velocity(k);
+      for (int it = 0; it < sc.vel_iters; ++it) {
+        bool changed = false;
+        for (int k = 0; k < ntc; ++k) changed |= contact_solve_velocity(k);
+        if (!changed) break;  // fixed point reached bit-for-bit: the remaining sweeps would all be no-ops
+      }
       {
         V2 cc = hc(b), vv = hv(b);
         float aa = ha(b), ww = hw(b);
@@ -1321,5 +1465,6 @@ struct Sim {
     return row_bits_from_ink(ink, sc.lcd_w);
   }
 };
+#undef sc
 
 }  // namespace blcd

@@ -46,7 +46,6 @@ __device__ __forceinline__ const DScene& stage_scene(const DScene* scene_g, unsi
   return *sc;
 }
 
-constexpr int kSceneBytes = (int)((sizeof(DScene) + 15) / 16 * 16);
 
 template <int BLOCK>
 __device__ __forceinline__ float* hot_base(unsigned char* smem_raw) {
@@ -92,7 +91,7 @@ __global__ void k_init(const DScene* scene_g, uint32_t* state, int64_t n) {
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_reset(const DScene* scene_g, uint32_t* state, int64_t n, uint64_t seed, int64_t world_offset,
                                                   const int64_t* idx, int64_t n_idx, const float* full_state) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* smem_raw = blcd_smem;
   const DScene& sc = stage_scene<BLOCK>(scene_g, smem_raw);
   int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (i >= n_idx) return;
@@ -110,7 +109,7 @@ __global__ void __launch_bounds__(BLOCK) k_reset(const DScene* scene_g, uint32_t
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_set_bodies(const DScene* scene_g, uint32_t* state, int64_t n, uint64_t seed, int64_t world_offset,
                                                        const float* bodies, const uint32_t* variants) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* smem_raw = blcd_smem;
   const DScene& sc = stage_scene<BLOCK>(scene_g, smem_raw);
   int64_t w = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (w >= n) return;
@@ -140,9 +139,9 @@ __global__ void k_get_bodies(const DScene* scene_g, const uint32_t* state, int64
 }
 
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_step(const DScene* scene_g, uint32_t* state, int64_t n, uint64_t seed, int64_t world_offset,
+__global__ void __launch_bounds__(BLOCK, 256 / BLOCK) k_step(const DScene* scene_g, uint32_t* state, int64_t n, uint64_t seed, int64_t world_offset,
                                                  const float* actions, int n_steps, OutPtrs out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* smem_raw = blcd_smem;
   const DScene& sc = stage_scene<BLOCK>(scene_g, smem_raw);
   int64_t w = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (w >= n) return;
@@ -163,9 +162,9 @@ __global__ void __launch_bounds__(BLOCK) k_step(const DScene* scene_g, uint32_t*
 }
 
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_rollout(const DScene* scene_g, uint32_t* state, int64_t n, uint64_t seed, int64_t world_offset,
+__global__ void __launch_bounds__(BLOCK, 256 / BLOCK) k_rollout(const DScene* scene_g, uint32_t* state, int64_t n, uint64_t seed, int64_t world_offset,
                                                     int T, OutPtrs out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* smem_raw = blcd_smem;
   const DScene& sc = stage_scene<BLOCK>(scene_g, smem_raw);
   int64_t w = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (w >= n) return;
@@ -185,7 +184,7 @@ __global__ void __launch_bounds__(BLOCK) k_rollout(const DScene* scene_g, uint32
 
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_observe(const DScene* scene_g, uint32_t* state, int64_t n, OutPtrs out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned char* smem_raw = blcd_smem;
   const DScene& sc = stage_scene<BLOCK>(scene_g, smem_raw);
   int64_t w = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (w >= n) return;
@@ -244,7 +243,6 @@ size_t smem_bytes(const blcd_env* h, int block) { return (size_t)kSceneBytes + (
 template <typename F>
 int launch_sized(blcd_env* h, F f) {
   switch (h->block) {
-    case 32: return f(std::integral_constant<int, 32>());
     case 64: return f(std::integral_constant<int, 64>());
     case 128: return f(std::integral_constant<int, 128>());
     default: return fail("unsupported block size");
@@ -293,7 +291,8 @@ int blcd_create(const blcd_spec* spec_host, int64_t n_worlds, int device, uint64
   CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   h->block = 64;
   if (const char* e = getenv("BLCD_BLOCK")) h->block = atoi(e);
-  while (h->block > 32 && smem_bytes(h, h->block) > (size_t)smem_max) h->block /= 2;
+  if (h->block != 64 && h->block != 128) h->block = 64;
+  while (h->block > 64 && smem_bytes(h, h->block) > (size_t)smem_max) h->block /= 2;
   if (smem_bytes(h, h->block) > (size_t)smem_max) { delete h; return fail("scene working set does not fit shared memory"); }
   CK(cudaMalloc(&h->scene_dev, sizeof(DScene)));
   CK(cudaMemcpy(h->scene_dev, &h->scene, sizeof(DScene), cudaMemcpyHostToDevice));
