@@ -72,15 +72,21 @@ BLCD_HD float normalize(V2& v) {
 struct Rot {
   float s, c;
 };
-BLCD_HD Rot rot_of(float a) {
-  Rot q;
 #ifdef __CUDA_ARCH__
+// b2Rot::Set.  One out-of-line copy: sincosf expands to ~100 instructions (fast path + large-argument slow path) and
+// is needed in ~30 places; inlining it everywhere made the kernel instruction-fetch bound.
+__device__ __noinline__ Rot rot_of(float a) {
+  Rot q;
   sincosf(a, &q.s, &q.c);
-#else
-  q.s = sinf(a); q.c = cosf(a);
-#endif
   return q;
 }
+#else
+inline Rot rot_of(float a) {
+  Rot q;
+  q.s = sinf(a); q.c = cosf(a);
+  return q;
+}
+#endif
 BLCD_HD Rot rot_identity() { Rot q; q.s = 0.0f; q.c = 1.0f; return q; }
 BLCD_HD V2 rmul(Rot q, V2 v) { return mk(q.c * v.x - q.s * v.y, q.s * v.x + q.c * v.y); }
 BLCD_HD V2 rmulT(Rot q, V2 v) { return mk(q.c * v.x + q.s * v.y, -q.s * v.x + q.c * v.y); }

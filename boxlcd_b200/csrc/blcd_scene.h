@@ -12,6 +12,7 @@ namespace blcd {
 
 enum { SH_CIRCLE = 0, SH_EDGE = 1, SH_POLY = 2 };
 constexpr int kMaxPairs = 64;
+constexpr int kMaxSlots = 16;   // manifold slots per world (upper bound)
 constexpr int kSlotWords = 16;   // one persistent manifold slot
 constexpr int kBodyWords = 13;   // cx cy a vx vy w sleepTime fat(lo.x lo.y hi.x hi.y) px py (b2Body::m_xf.p)
 constexpr int kJointWords = 6;   // impulse xyz, motorImpulse, motorSpeed, limitState
@@ -298,13 +299,13 @@ inline const char* build_scene(DScene& sc, const blcd_spec& sp, int maxm) {
   sc.off_slots = sc.off_clist + sc.clist_words;
   sc.off_cnt = sc.off_slots + kSlotWords * sc.maxm;
   sc.state_words = sc.off_cnt + BLCD_N_COUNTERS;
-  // shared-memory layout: velocities and positions of nb dynamic rows + 1 static row, mass rows, joints, contacts
+  // shared-memory layout: velocities and positions of nb dynamic rows + 1 static row, inverse-mass rows
   sc.h_vel = 0;
   sc.h_pos = sc.h_vel + 3 * (sc.nb + 1);
   sc.h_mass = sc.h_pos + 3 * (sc.nb + 1);
-  sc.h_joint = sc.h_mass + 2 * (sc.nb + 1);
-  sc.h_con = sc.h_joint + kHotJoint * sc.nj;
-  sc.hot_words = sc.h_con + kHotCon * sc.maxm;
+  sc.h_joint = 0;   // joint and contact records are thread-local (blcd_world.cuh), not in shared memory
+  sc.h_con = 0;
+  sc.hot_words = sc.h_mass + 2 * (sc.nb + 1);
   return nullptr;
 }
 

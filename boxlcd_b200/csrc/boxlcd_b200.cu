@@ -245,6 +245,7 @@ int launch_sized(blcd_env* h, F f) {
   switch (h->block) {
     case 64: return f(std::integral_constant<int, 64>());
     case 128: return f(std::integral_constant<int, 128>());
+    case 256: return f(std::integral_constant<int, 256>());
     default: return fail("unsupported block size");
   }
 }
@@ -252,6 +253,9 @@ int launch_sized(blcd_env* h, F f) {
 template <typename K>
 int set_smem_attr(K kernel, size_t bytes) {
   CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  // the rest of the 256 KB on-chip array serves as L1 for the thread-local constraint records
+  int pct = (int)((bytes + 1024) * 100 / (228 * 1024)) + 1;
+  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct));
   return 0;
 }
 
@@ -280,18 +284,20 @@ int blcd_create(const blcd_spec* spec_host, int64_t n_worlds, int device, uint64
   blcd_env* h = new blcd_env();
   // manifold slots per world: enough for every touching pair seen in long random rollouts of the reference scenes
   // (tests/test_hostsim_vs_oracle.py measures it); overflow is counted in BLCD_CNT_OVERFLOW, never silent
-  int maxm = spec_host->n_bodies <= 2 ? 4 : (spec_host->n_bodies <= 4 ? 6 : (spec_host->n_bodies == 5 ? 8 : 16));
+  int maxm = spec_host->n_bodies <= 2 ? 4 : (spec_host->n_bodies <= 4 ? 8 : (spec_host->n_bodies == 5 ? 12 : 16));
   if (const char* e = getenv("BLCD_MAX_MANIFOLDS")) maxm = atoi(e);
-  if (maxm < 1 || maxm > 16) { delete h; return fail("BLCD_MAX_MANIFOLDS must be in 1..16"); }
+  if (maxm < 1 || maxm > kMaxSlots) { delete h; return fail("BLCD_MAX_MANIFOLDS must be in 1..16"); }
   const char* err = host::build_scene(h->scene, *spec_host, maxm);
   if (err) { delete h; return fail(std::string("blcd_create: ") + err); }
   h->n = n_worlds; h->device = device; h->seed = seed; h->world_offset = world_offset;
   // block size: largest of 128/64/32 that still lets several blocks share an SM's shared memory
   int smem_max = 0;
   CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  h->block = 64;
+  // one 256-thread block per SM: the register file (<= 255 registers x 256 threads) is the occupancy limit, and all eight
+  // warps of the block walk the solver phases together (Sim::phase_align)
+  h->block = 256;
   if (const char* e = getenv("BLCD_BLOCK")) h->block = atoi(e);
-  if (h->block != 64 && h->block != 128) h->block = 64;
+  if (h->block != 64 && h->block != 128 && h->block != 256) h->block = 256;
   while (h->block > 64 && smem_bytes(h, h->block) > (size_t)smem_max) h->block /= 2;
   if (smem_bytes(h, h->block) > (size_t)smem_max) { delete h; return fail("scene working set does not fit shared memory"); }
   CK(cudaMalloc(&h->scene_dev, sizeof(DScene)));

@@ -20,7 +20,7 @@ extern "C" {
 
 void* hostsim_new(const blcd_spec* spec, int64_t n, uint64_t seed, int64_t offset, int maxm) {
   HostSim* h = new HostSim();
-  if (maxm <= 0) maxm = spec->n_bodies <= 2 ? 4 : (spec->n_bodies <= 4 ? 6 : (spec->n_bodies == 5 ? 8 : 16));  // same default as blcd_create
+  if (maxm <= 0) maxm = spec->n_bodies <= 2 ? 4 : (spec->n_bodies <= 4 ? 8 : (spec->n_bodies == 5 ? 12 : 16));  // same default as blcd_create
   if (host::build_scene(h->scene, *spec, maxm)) { delete h; return nullptr; }
   h->n = n; h->seed = seed; h->offset = offset;
   h->state.assign((size_t)h->scene.state_words * n, 0u);
