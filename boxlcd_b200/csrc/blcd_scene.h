@@ -65,6 +65,7 @@ struct DScene {
   float dt;
   V2 gravity;
   int32_t maxm;  // manifold slots per world
+  int32_t align_mode;  // block-level phase alignment points: 0 none, 1 velocity loop, 2 + position loop, 3 + sub-step start and TOI, 4 + write-back, 5 + env step
   // per-world state layout in HBM: word i of world w lives at state[i * n_worlds + w]
   int32_t off_misc, off_joint, off_clist, clist_words, off_slots, off_cnt, state_words;
   // per-thread shared-memory layout (words), see blcd_world.cuh
@@ -292,6 +293,7 @@ inline const char* build_scene(DScene& sc, const blcd_spec& sp, int maxm) {
     }
   }
   sc.maxm = maxm;
+  sc.align_mode = 4;
   sc.off_misc = kBodyWords * sc.nb;
   sc.off_joint = sc.off_misc + kMiscWords;
   sc.off_clist = sc.off_joint + kJointWords * sc.nj;

@@ -1150,7 +1150,7 @@ struct Sim {
     for (int k = 0; k < nc; ++k) contact_warm_start(k);
     for (int k = 0; k < njo; ++k) joint_init(jorder[k], jisl[k], dtRatio, h_dt);
     const int vi = sc.vel_iters;
-    phase_align();
+    if (sc.align_mode >= 1) phase_align(); else reconverge();
     if (njo <= 3) {
       // up to three joints (every reference robot in scope) live in registers for the whole loop; contacts, whose
       // number is data dependent, stay in shared memory
@@ -1193,7 +1193,7 @@ struct Sim {
       set_hv(b, vv, ww);
     }
     // position iterations; every island stops on its own convergence
-    phase_align();
+    if (sc.align_mode >= 2) phase_align(); else reconverge();
     uint32_t islDone = 0u;
     const uint32_t islAll = (1u << nIslands) - 1u;
     for (int it = 0; it < sc.pos_iters && islDone != islAll; ++it) {
@@ -1213,7 +1213,7 @@ struct Sim {
       islDone |= ~bad & islAll;
     }
     // write back + SynchronizeTransform
-    reconverge();
+    if (sc.align_mode >= 4) phase_align(); else reconverge();
     Xf xf1[BLCD_MAX_BODIES];
     for (int b = 0; b < nb; ++b) {
       if (islandOf[b] < 0) continue;
@@ -1417,7 +1417,7 @@ struct Sim {
   // ---- b2World::Step -------------------------------------------------------------------------------------------------
   BLCD_HD void b2_step() {
     const float dt = sc.dt;
-    reconverge();
+    if (sc.align_mode >= 3) phase_align(); else reconverge();
     if (newFixture) {
       find_new_contacts((1u << (sc.nw + sc.nb)) - 1u);
       newFixture = false;
@@ -1425,7 +1425,7 @@ struct Sim {
     float dtRatio = inv_dt0 * dt;
     collide();
     solve(dt, dtRatio);
-    reconverge();
+    if (sc.align_mode >= 3) phase_align(); else reconverge();
     if (!(sc.flags & BLCD_FLAG_NO_TOI)) solve_toi(dt);
     reconverge();
     inv_dt0 = 1.0f / dt;
@@ -1437,6 +1437,7 @@ struct Sim {
 
   // WorldEnv.step (world_env.py:431-452): motor speeds from the clipped action, then n_substeps world steps
   BLCD_HD void env_step(const float* action) {
+    if (sc.align_mode >= 5) phase_align();
     ep_t += 1;
     for (int j = 0; j < sc.nj; ++j) {
       const DJoint& jd = sc.joint[j];

@@ -139,7 +139,7 @@ __global__ void k_get_bodies(const DScene* scene_g, const uint32_t* state, int64
 }
 
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, 256 / BLOCK) k_step(const DScene* scene_g, uint32_t* state, int64_t n, uint64_t seed, int64_t world_offset,
+__global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 1 : 256 / BLOCK) k_step(const DScene* scene_g, uint32_t* state, int64_t n, uint64_t seed, int64_t world_offset,
                                                  const float* actions, int n_steps, OutPtrs out) {
   unsigned char* smem_raw = blcd_smem;
   const DScene& sc = stage_scene<BLOCK>(scene_g, smem_raw);
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(BLOCK, 256 / BLOCK) k_step(const DScene* scene
 }
 
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, 256 / BLOCK) k_rollout(const DScene* scene_g, uint32_t* state, int64_t n, uint64_t seed, int64_t world_offset,
+__global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 1 : 256 / BLOCK) k_rollout(const DScene* scene_g, uint32_t* state, int64_t n, uint64_t seed, int64_t world_offset,
                                                     int T, OutPtrs out) {
   unsigned char* smem_raw = blcd_smem;
   const DScene& sc = stage_scene<BLOCK>(scene_g, smem_raw);
@@ -246,6 +246,8 @@ int launch_sized(blcd_env* h, F f) {
     case 64: return f(std::integral_constant<int, 64>());
     case 128: return f(std::integral_constant<int, 128>());
     case 256: return f(std::integral_constant<int, 256>());
+    case 384: return f(std::integral_constant<int, 384>());
+    case 512: return f(std::integral_constant<int, 512>());
     default: return fail("unsupported block size");
   }
 }
@@ -289,6 +291,7 @@ int blcd_create(const blcd_spec* spec_host, int64_t n_worlds, int device, uint64
   if (maxm < 1 || maxm > kMaxSlots) { delete h; return fail("BLCD_MAX_MANIFOLDS must be in 1..16"); }
   const char* err = host::build_scene(h->scene, *spec_host, maxm);
   if (err) { delete h; return fail(std::string("blcd_create: ") + err); }
+  if (const char* e = getenv("BLCD_ALIGN")) h->scene.align_mode = atoi(e);
   h->n = n_worlds; h->device = device; h->seed = seed; h->world_offset = world_offset;
   // block size: largest of 128/64/32 that still lets several blocks share an SM's shared memory
   int smem_max = 0;
@@ -297,7 +300,7 @@ int blcd_create(const blcd_spec* spec_host, int64_t n_worlds, int device, uint64
   // warps of the block walk the solver phases together (Sim::phase_align)
   h->block = 256;
   if (const char* e = getenv("BLCD_BLOCK")) h->block = atoi(e);
-  if (h->block != 64 && h->block != 128 && h->block != 256) h->block = 256;
+  if (h->block != 64 && h->block != 128 && h->block != 256 && h->block != 384 && h->block != 512) h->block = 256;
   while (h->block > 64 && smem_bytes(h, h->block) > (size_t)smem_max) h->block /= 2;
   if (smem_bytes(h, h->block) > (size_t)smem_max) { delete h; return fail("scene working set does not fit shared memory"); }
   CK(cudaMalloc(&h->scene_dev, sizeof(DScene)));
