@@ -137,8 +137,8 @@ def run_reference(a, rank, world_size):
   line = {
       'impl': 'reference', 'metric': 'env-steps/sec incl. LCD frames', 'value': value, 'unit': 'env-steps/s', 'n_gpus': a.gpus, 'steps': a.steps,
       'warmup': a.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-      'config': {'workload': f'envs.{a.env}() {sp.lcd_h}x{sp.lcd_w}, random-action {T}-step rollouts (reset + step + obs + frame)',
-                 'worlds_per_step': per_step, 'T': T, 'note': 'CPU restatement of Box2D 2.3 + PIL rasterizer (oracle/), not pybox2d: pybox2d is not installable here'},
+      'config': {'workload': f'envs.{a.env}() {sp.lcd_h}x{sp.lcd_w}, {a.worlds} worlds per GPU, random-action {T}-step rollouts (reset + step + obs + frame)',
+                 'worlds_per_gpu': a.worlds, 'sample_worlds_per_step': per_step, 'T': T, 'note': 'CPU restatement of Box2D 2.3 + PIL rasterizer (oracle/), not pybox2d: pybox2d is not installable here'},
       'cpu_baseline': {'value': value, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port', 'sample': f'{per_step} worlds x {T} env-steps per step'},
       'e2e': {'value': value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
       'gpu_launches': 0,

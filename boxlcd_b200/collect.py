@@ -53,6 +53,24 @@ def parse_args(argv=None):
   return AttrDict(parser.parse_args(argv).__dict__)
 
 
+def shard_range(n_items, rank, world):
+  """contiguous [lo, hi) of n_items owned by `rank` of `world` (rollouts are keyed by their global index, so the
+  dataset does not depend on the number of ranks)"""
+  return n_items * rank // world, n_items * (rank + 1) // world
+
+
+def gather_shards(data, rank, world):
+  """final gather of per-rank dataset shards on rank 0 -- the only collective on this path"""
+  if world == 1:
+    return data
+  import torch.distributed as dist
+  parts = [None] * world if rank == 0 else None
+  dist.gather_object(data, parts, dst=0)
+  if rank != 0:
+    return None
+  return {k: np.concatenate([p[k] for p in parts]) for k in data}
+
+
 def collect_arrays(env, n_rollouts, T, batch=65536, seed=0, device=None, world_offset=0, progress=None):
   """n_rollouts x T random-action rollouts of `env` -> dict of host arrays in the reference layout."""
   import torch
@@ -108,14 +126,9 @@ def main(argv=None):
       np.savez_compressed(logdir / f'{stamp}-{T}.barrel', **data)
   else:
     N = G.collect_n
-    lo, hi = N * rank // world, N * (rank + 1) // world
+    lo, hi = shard_range(N, rank, world)
     data = collect_arrays(env, hi - lo, T, G.batch, G.seed, world_offset=lo, progress=say)
-    if world > 1:
-      import torch.distributed as dist
-      parts = [None] * world if rank == 0 else None
-      dist.gather_object(data, parts, dst=0)   # final gather of dataset shards: the only collective on this path
-      if rank == 0:
-        data = {k: np.concatenate([p[k] for p in parts]) for k in data}
+    data = gather_shards(data, rank, world)
     if rank == 0:
       os.makedirs('rollouts', exist_ok=True)
       np.savez_compressed(f'rollouts/{G.env}-{N}.npz', **data)

@@ -64,17 +64,21 @@ __device__ __forceinline__ void write_obs(const Sim<BLOCK>& sim, const DScene& s
         for (int k = 0; k < 4; ++k) fs[sc.body[b].obs[k]] = ob[k];
       }
     }
-    if (o.full_state)
-      for (int i = 0; i < sc.S; ++i) o.full_state[row * sc.S + i] = fs[i];
+    // dataset rows are written once and never read back by the kernel: streaming stores (evict-first) keep them from
+    // pushing the thread-local solver records out of L2
+    if (o.full_state) {
+      float4* dst = reinterpret_cast<float4*>(o.full_state + row * sc.S);   // S = 4 * n_bodies, rows are 16-byte aligned
+      for (int i = 0; i < sc.S / 4; ++i) __stcs(dst + i, make_float4(fs[4 * i], fs[4 * i + 1], fs[4 * i + 2], fs[4 * i + 3]));
+    }
     if (o.proprio) {
       if (sc.P == 0) o.proprio[row] = 0.0f;
-      for (int i = 0; i < sc.P; ++i) o.proprio[row * sc.P + i] = fs[sc.pobs[i]];
+      for (int i = 0; i < sc.P; ++i) __stcs(o.proprio + row * sc.P + i, fs[sc.pobs[i]]);
     }
   }
   if (o.lcd_bits || o.lcd_bool) {
     for (int R = 0; R < sc.lcd_h; ++R) {
       uint32_t bits = sim.lcd_row(R);
-      if (o.lcd_bits) o.lcd_bits[row * sc.lcd_h + R] = bits;
+      if (o.lcd_bits) __stcs(o.lcd_bits + row * sc.lcd_h + R, bits);
       if (o.lcd_bool)
         for (int x = 0; x < sc.lcd_w; ++x) o.lcd_bool[(row * sc.lcd_h + R) * sc.lcd_w + x] = (uint8_t)((bits >> x) & 1u);
     }
@@ -176,7 +180,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 1 : 256 / BLOCK) k_rollo
     write_obs<BLOCK>(sim, sc, out, row);   // obs_t is recorded before action t (collect.py:33-39)
     sim.draw_action(act);
     if (out.actions)
-      for (int k = 0; k < sc.A; ++k) out.actions[row * sc.A + k] = act[k];
+      for (int k = 0; k < sc.A; ++k) __stcs(out.actions + row * sc.A + k, act[k]);
     sim.env_step(act);
   }
   sim.store();
