@@ -142,6 +142,21 @@ __global__ void k_get_bodies(const DScene* scene_g, const uint32_t* state, int64
   }
 }
 
+// b2Transform of every dynamic body exactly as the simulation holds it (position, sincosf(angle)): what lcd_render consumes
+__global__ void k_get_poses(const DScene* scene_g, const uint32_t* state, int64_t n, float* poses, uint32_t* variants) {
+  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n) return;
+  const DScene& sc = *scene_g;
+  const float* sf = reinterpret_cast<const float*>(state);
+  for (int b = 0; b < sc.nb; ++b) {
+    int o = kBodyWords * b;
+    Rot q = rot_of(sf[(int64_t)(o + 2) * n + w]);
+    float* dst = poses + (w * sc.nb + b) * 4;
+    dst[0] = sf[(int64_t)(o + 11) * n + w]; dst[1] = sf[(int64_t)(o + 12) * n + w]; dst[2] = q.s; dst[3] = q.c;
+  }
+  if (variants) variants[w] = (state[(int64_t)sc.off_misc * n + w] >> kVariantShift) & 0xFFu;
+}
+
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 1 : 256 / BLOCK) k_step(const DScene* scene_g, uint32_t* state, int64_t n, uint64_t seed, int64_t world_offset,
                                                  const float* actions, int n_steps, OutPtrs out) {
@@ -387,6 +402,15 @@ int blcd_get_bodies(blcd_handle h, float* bodies_dev, uint64_t stream) {
   if (!h || !bodies_dev) return fail("blcd_get_bodies: bad arguments");
   CK(cudaSetDevice(h->device));
   k_get_bodies<<<(unsigned)((h->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(h->scene_dev, h->state, h->n, bodies_dev);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+int blcd_get_poses(blcd_handle h, float* poses_dev, uint32_t* variant_dev, uint64_t stream) {
+  if (!h || !poses_dev) return fail("blcd_get_poses: bad arguments");
+  CK(cudaSetDevice(h->device));
+  k_get_poses<<<(unsigned)((h->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(h->scene_dev, h->state, h->n, poses_dev, variant_dev);
   CK(cudaGetLastError());
   h->launches += 1;
   return 0;

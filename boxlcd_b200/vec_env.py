@@ -69,6 +69,8 @@ class VecWorldEnv:
   def reset_dev(self, idx=None, full_state=None):
     """idx: int64 device tensor of world indices (None = all); full_state: [len(idx) or N, S] float32 device tensor"""
     n = 0 if idx is None else idx.numel()
+    if idx is not None and n == 0:
+      return   # an empty index list resets nothing (a NULL index pointer would mean "all worlds" at the C ABI)
     _lib.check(self.l.blcd_reset(self.h, _ptr(idx), n, _ptr(full_state), self._stream()))
 
   def step_dev(self, actions=None, observe=True):
@@ -111,6 +113,13 @@ class VecWorldEnv:
     out = torch.empty((self.n, self.B, 6), dtype=torch.float32, device=self.device)
     _lib.check(self.l.blcd_get_bodies(self.h, _ptr(out), self._stream()))
     return out.cpu().numpy()
+
+  def get_poses_dev(self):
+    """(poses [N, B, 4] float32 = x, y, sin, cos; variants [N] int32) exactly as the rasterizer sees them"""
+    poses = torch.empty((self.n, self.B, 4), dtype=torch.float32, device=self.device)
+    variants = torch.empty((self.n,), dtype=torch.int32, device=self.device)
+    _lib.check(self.l.blcd_get_poses(self.h, _ptr(poses), _ptr(variants), self._stream()))
+    return poses, variants
 
   def counters(self):
     out = torch.empty((self.n, 8), dtype=torch.int32, device=self.device)
@@ -174,12 +183,8 @@ class VecWorldEnv:
     height = height or self.H
     if (width, height) == (self.W, self.H):
       return self.unpack_lcd(self.observe_dev()['lcd_bits']).cpu().numpy()
-    if any(self.spec.bodies[b].n_variants > 1 for b in range(self.B)):
-      raise NotImplementedError('resized frames of scenes with shape="random" objects are not built yet')
     if width > 32:
       raise NotImplementedError('frames wider than 32 px need the tiled rasterizer path (not built)')
-    b = torch.as_tensor(self.get_bodies()).to(self.device)
-    poses = torch.stack([b[..., 0], b[..., 1], torch.sin(b[..., 2].double()).float(), torch.cos(b[..., 2].double()).float()], -1).contiguous()
-    variants = None
+    poses, variants = self.get_poses_dev()
     bits = self.render_poses_dev(poses, variants, width, height)
     return self.unpack_lcd(bits, width).cpu().numpy()

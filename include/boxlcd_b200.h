@@ -161,6 +161,9 @@ int blcd_render_poses_sized(blcd_handle h, const float* poses_dev, const uint32_
  * the protocol single-step parity is defined on (last paragraph). */
 int blcd_set_bodies(blcd_handle h, const float* bodies_dev, const uint32_t* variant_dev, uint64_t stream);
 int blcd_get_bodies(blcd_handle h, float* bodies_dev, uint64_t stream);
+/* b2Transform of every dynamic body as lcd_render consumes it: poses [N, n_bodies, 4] = (x, y, sin, cos); variant_dev
+ * (optional, [N]) receives the shape-variant bitmask.  Feeding both to blcd_render_poses reproduces blcd_observe's frames. */
+int blcd_get_poses(blcd_handle h, float* poses_dev, uint32_t* variant_dev, uint64_t stream);
 
 /* Checkpoint / restore of the complete per-world simulation state (poses, velocities, warm-start impulses, contact
  * slots, RNG counters).  blcd_state_bytes() gives the buffer size for this handle. */

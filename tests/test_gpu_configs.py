@@ -1,0 +1,182 @@
+"""BASELINE.json's configs as GPU test cases (full sizes where the check is a size-independent property), the dataset
+formats of examples/collect.py / research/data.py, and edge cases (ragged batch sizes, empty / partial resets, errors)."""
+import os
+import numpy as np
+import pytest
+import torch
+import boxlcd_b200 as blcd
+from oracle import oracle
+from common import make_env
+
+pytestmark = pytest.mark.gpu
+
+
+def vec(env, n, **kw):
+  from boxlcd_b200.vec_env import VecWorldEnv
+  return VecWorldEnv(env, n, **kw)
+
+
+def check_world_invariants(env, v, slack=0.12):
+  b = v.get_bodies()
+  assert np.isfinite(b).all()
+  assert (b[..., 0] > -slack).all() and (b[..., 0] < env.WIDTH + slack).all()
+  assert (b[..., 1] > -slack).all() and (b[..., 1] < env.HEIGHT + slack).all()
+  assert v.counters()[:, 5].sum() == 0, 'manifold slots overflowed'
+  return b
+
+
+def frames_match_oracle_rasterizer(env, v, sample=4096, seed=0):
+  """frames written by the fused kernel == oracle rasterizer applied to the kernel's own transforms (bit-exact)"""
+  obs = v.observe_dev()
+  bits = obs['lcd_bits'].cpu().numpy().view(np.uint32)
+  poses, variants = v.get_poses_dev()
+  idx = np.random.RandomState(seed).choice(v.n, min(sample, v.n), replace=False)
+  ow = oracle.OracleWorlds(env.layout.spec, 1)
+  ow.reset()
+  shapes = ow.lcd_shapes(0)
+  if any(env.layout.spec.bodies[k].n_variants > 1 for k in range(v.B)):
+    pytest.skip('per-world shapes')
+  ref = oracle.lcd_render(shapes, poses.cpu().numpy()[idx], env.WIDTH, v.W, v.H)
+  assert (bits[idx] == ref).all()
+
+
+def test_config0_dropbox_200_step_collect_format(tmp_path, monkeypatch):
+  """envs.Dropbox() 16x16, random actions, 200-step rollouts via collect (examples/collect.py:24-41)"""
+  from boxlcd_b200 import collect
+  monkeypatch.chdir(tmp_path)
+  collect.main(['--env=Dropbox', '--collect_n=300', '--ep_len=200', '--batch=128'])
+  d = np.load(tmp_path / 'rollouts' / 'Dropbox-300.npz')
+  assert set(d.files) == {'action', 'full_state', 'proprio', 'lcd'}
+  assert d['action'].shape == (300, 200, 1) and d['action'].dtype == np.float64
+  assert d['full_state'].shape == (300, 200, 4) and d['full_state'].dtype == np.float32
+  assert d['proprio'].shape == (300, 200, 1) and d['proprio'].dtype == np.float32 and (d['proprio'] == 0).all()
+  assert d['lcd'].shape == (300, 200, 16, 16) and d['lcd'].dtype == np.bool_
+  assert d['action'].min() >= -1 and d['action'].max() <= 1
+  ink = (~d['lcd']).sum((2, 3))
+  assert ink.min() >= 16 and ink.max() <= 40        # the 1.4 m (4.48 px) box covers 18..36 px depending on its angle
+  last = ~d['lcd'][:, -1]
+  rows = last.any(2)
+  assert (rows[:, :9] == False).all() and rows[:, 11:].all()   # at rest on the floor: rows 11-15
+  assert np.isin(last.sum((1, 2)), [24, 25, 30]).mean() > 0.9  # flat on the floor: a 5x5 or 5x6 block (oracle: 99 %)
+  # element [i, j] is the observation BEFORE action j: consecutive observations differ while the box is falling
+  assert (np.abs(np.diff(d['full_state'][:, :5], axis=1)).max(2) > 0).any()
+
+
+def test_config1_bounce2_65k_worlds():
+  env = make_env('Bounce2')
+  v = vec(env, 65536, seed=2)
+  v.reset_dev()
+  r = v.rollout_dev(50)
+  b = check_world_invariants(env, v)
+  bits = r['lcd_bits'].cpu().numpy().view(np.uint32)
+  ink = (~oracle.unpack_bits(bits[::64], 16)).sum((2, 3))
+  assert ink.min() >= 8 and ink.max() <= 44 and 20 < ink.mean() < 30   # two r=0.5 balls, 12-16 px each (gif: 24.5 mean)
+  frames_match_oracle_rasterizer(env, v)
+  # balls do not overlap by more than the solver's slop
+  d = np.hypot(b[:, 0, 0] - b[:, 1, 0], b[:, 0, 1] - b[:, 1, 1])
+  assert (d > 1.0 - 0.05).mean() > 0.999
+
+
+def test_config2_urchin_262k_worlds():
+  env = make_env('Urchin')
+  v = vec(env, 262144, seed=3)
+  v.reset_dev()
+  v.rollout_dev(10)
+  b = check_world_invariants(env, v)
+  for leg in (1, 2, 3):   # revolute anchors stay pinned to the root
+    ax = b[:, leg, 0] - np.sin(b[:, leg, 2]) * (20 / 30)
+    ay = b[:, leg, 1] + np.cos(b[:, leg, 2]) * (20 / 30)
+    err = np.hypot(ax - b[:, 0, 0], ay - b[:, 0, 1])
+    # Box2D's TOI sub-steps ignore joints, so a leg that slams a wall can be pulled a few cm off its hinge for a step;
+    # the CPU oracle gives the same distribution (97.3-97.9 % below 3 cm, 99.7 % below 10 cm after 10 random steps)
+    assert 0.96 < (err < 0.03).mean() < 0.99 and (err < 0.1).mean() > 0.995
+  frames_match_oracle_rasterizer(env, v)
+  c = v.counters().astype(np.int64)
+  assert (c[:, 7] == 30).all()   # 10 env steps x 3 sub-steps for every world
+
+
+def test_config3_luxocube_barrel_dataset(tmp_path):
+  """research/data.py barrel format: 1000 rollouts per file, {timestamp}-{ep_len}.barrel.npz under logdir/<split>/"""
+  from boxlcd_b200 import collect
+  collect.main(['--env=LuxoCube', '--barrels=2', f'--logdir={tmp_path}', '--split=test'])
+  files = sorted((tmp_path / 'test').glob('*.barrel.npz'))
+  assert len(files) == 2 and all(f.name.endswith('-150.barrel.npz') for f in files)
+  d = np.load(files[0])
+  assert d['action'].shape == (1000, 150, 3) and d['action'].dtype == np.float64
+  assert d['full_state'].shape == (1000, 150, 20) and d['proprio'].shape == (1000, 150, 16) and d['lcd'].shape == (1000, 150, 16, 24)
+  env = make_env('LuxoCube')
+  assert (d['proprio'] == d['full_state'][..., env.pobs_idxs]).all()
+  d2 = np.load(files[1])
+  assert not (d['action'][:10] == d2['action'][:10]).all(), 'barrels must hold different rollouts'
+  ink = (~d['lcd']).sum((2, 3))
+  assert 38 < ink.mean() < 50   # reference gif: 43.4 mean
+
+
+@pytest.mark.parametrize('n', [4096, 16384])
+def test_config4_urchinball_sweep_sizes(n):
+  env = make_env('UrchinBall')
+  v = vec(env, n, seed=6)
+  v.reset_dev()
+  v.rollout_dev(15)
+  check_world_invariants(env, v)
+  frames_match_oracle_rasterizer(env, v, sample=2048)
+
+
+@pytest.mark.parametrize('n', [1, 33, 257, 1000])
+def test_ragged_batch_sizes_match_oracle(n):
+  """batch sizes that leave partial warps / partial blocks (the phase barriers count live warps only)"""
+  env = make_env('Urchin')
+  v = vec(env, n, seed=8)
+  ow = oracle.OracleWorlds(env.layout.spec, n, seed=8, threads=4)
+  v.reset_dev(); ow.reset()
+  rg = v.rollout_dev(3)
+  ro = ow.rollout(3)
+  assert (rg['action'].cpu().numpy() == ro['action']).all()
+  assert (np.abs(rg['full_state'].cpu().numpy()[:, 1] - ro['full_state'][:, 1]).max(1) < 1e-4).mean() >= 0.95
+  assert np.isfinite(v.get_bodies()).all()
+
+
+def test_partial_and_empty_reset():
+  env = make_env('Bounce2')
+  v = vec(env, 64, seed=1)
+  v.reset_dev()
+  v.rollout_dev(5)
+  before = v.get_bodies()
+  v.reset_dev(torch.zeros(0, dtype=torch.int64, device='cuda'))        # empty index list: nothing happens
+  assert (v.get_bodies() == before).all()
+  idx = torch.tensor([3, 17, 40], dtype=torch.int64, device='cuda')
+  v.reset_dev(idx)
+  after = v.get_bodies()
+  keep = np.setdiff1d(np.arange(64), [3, 17, 40])
+  assert (after[keep] == before[keep]).all() and (after[[3, 17, 40]] != before[[3, 17, 40]]).any()
+  assert (after[[3, 17, 40], :, 3:] == 0).all()   # fresh worlds start at rest
+
+
+def test_errors_are_loud():
+  env = make_env('Urchin')
+  v = vec(env, 8)
+  with pytest.raises(NotImplementedError):
+    v.render(64, 32)
+  with pytest.raises(RuntimeError, match='frame width'):
+    poses, var = v.get_poses_dev()
+    v.render_poses_dev(poses, None, 40, 16)
+  with pytest.raises(NotImplementedError):
+    blcd.envs.Urchin({'walls': 0})
+  with pytest.raises(NotImplementedError):
+    blcd.envs.Urchin().lcd_render(lcd_mode='RGB')
+
+
+def test_object2_random_shapes_render_and_step():
+  env = make_env('Object2')
+  n = 4096
+  v = vec(env, n, seed=5)
+  ow = oracle.OracleWorlds(env.layout.spec, n, seed=5, threads=8)
+  v.reset_dev(); ow.reset()
+  poses, variants = v.get_poses_dev()
+  _, var_o = ow.get_poses()
+  assert (variants.cpu().numpy().view(np.uint32) == var_o).all()
+  assert 0.2 < (var_o & 1).mean() < 0.8        # both shapes occur
+  og, oo = v.observe(), ow.observe()
+  assert (og['lcd'] == oracle.unpack_bits(oo['lcd_bits'], 16)).all((1, 2)).mean() > 0.999
+  v.rollout_dev(20); ow.rollout(20, want=())
+  assert np.isfinite(v.get_bodies()).all()
