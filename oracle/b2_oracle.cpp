@@ -162,6 +162,7 @@ void sample_poses(Env& env, const blcd_spec& sp, float (*pose)[3]) {
       angle64[b] = ang;
       pose[b][0] = f32(x); pose[b][1] = f32(y); pose[b][2] = f32(ang);
     } else if (bd.role == BLCD_ROLE_CHILD) {
+      // world_env.py:230-252: children hang off their parent by the joint anchors; the joint angle is relative to the ROOT
       double mangle = angle64[bd.root] + bd.joint_angle;
       mangle = atan2(sin(mangle), cos(mangle));
       angle64[b] = mangle;
@@ -417,6 +418,35 @@ int blcd_oracle_worlds_rollout(void* h, int32_t T, float* full_state, uint32_t* 
 int blcd_oracle_worlds_counters(void* h, uint32_t* counters) {
   Batch* b = (Batch*)h;
   for (size_t i = 0; i < b->envs.size(); ++i) write_counters(b->envs[i], counters + i * BLCD_N_COUNTERS);
+  return 0;
+}
+
+// child placement algebra only (world_env.py:230-252): given the pose (x, y, angle) of every ROOT / OBJECT body in
+// pose_in [n_bodies][3] (children ignored), writes all poses with the children placed.  angle is taken as float64 from
+// the float32 input, like `root_angle` held in Python.
+int blcd_oracle_place_children(const blcd_spec* sp, const double* pose_in, float* pose_out) {
+  double angle64[BLCD_MAX_BODIES] = {0};
+  float pose[BLCD_MAX_BODIES][3];
+  for (int b = 0; b < sp->n_bodies; ++b) {
+    const blcd_body_def& bd = sp->bodies[b];
+    if (bd.role != BLCD_ROLE_CHILD) {
+      angle64[b] = pose_in[b * 3 + 2];
+      pose[b][0] = f32(pose_in[b * 3]); pose[b][1] = f32(pose_in[b * 3 + 1]); pose[b][2] = f32(pose_in[b * 3 + 2]);
+    } else {
+      double mangle = angle64[bd.root] + bd.joint_angle;
+      mangle = atan2(sin(mangle), cos(mangle));
+      angle64[b] = mangle;
+      double pangle = angle64[bd.parent];
+      double aax = cos(pangle) * bd.anchor_a[0] - sin(pangle) * bd.anchor_a[1];
+      double aay = sin(pangle) * bd.anchor_a[0] + cos(pangle) * bd.anchor_a[1];
+      double abx = cos(mangle) * bd.anchor_b[0] - sin(mangle) * bd.anchor_b[1];
+      double aby = sin(mangle) * bd.anchor_b[0] + cos(mangle) * bd.anchor_b[1];
+      float px = pose[bd.parent][0] + f32(aax), py = pose[bd.parent][1] + f32(aay);
+      px = px - f32(abx); py = py - f32(aby);
+      pose[b][0] = px; pose[b][1] = py; pose[b][2] = f32(mangle);
+    }
+  }
+  for (int b = 0; b < sp->n_bodies; ++b) { pose_out[b * 3] = pose[b][0]; pose_out[b * 3 + 1] = pose[b][1]; pose_out[b * 3 + 2] = pose[b][2]; }
   return 0;
 }
 

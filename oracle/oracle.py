@@ -172,3 +172,13 @@ class OracleWorlds:
     out = np.zeros(4, np.float32)
     self.l.blcd_oracle_worlds_mass(self.h, i, k, _p(out))
     return out
+
+
+def place_children(spec, pose_in):
+  """world_env.py:230-252 on given root / object poses [B, 3] (float64) -> all poses [B, 3] float32"""
+  l = _bind_worlds(lib())
+  l.blcd_oracle_place_children.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+  pin = np.ascontiguousarray(pose_in, np.float64)
+  out = np.zeros((spec.n_bodies, 3), np.float32)
+  l.blcd_oracle_place_children(C.byref(spec), _p(pin), _p(out))
+  return out

@@ -118,6 +118,7 @@ class FakeBody:
   def __init__(self, position=(0, 0), angle=0.0, fixtures=None, sc=None, **kw):
     self._pos = _Vec2(position)
     self._angle = float(F(angle))
+    kw['_angle64'] = float(angle)   # the float64 Python value before pybox2d stores it as float32
     self._sc = sc  # optional explicit (sin, cos) fp32 pair overriding sinf/cosf(angle)
     self.fixtures = fixtures if isinstance(fixtures, (list, tuple)) else [fixtures]
     self.kw = kw
