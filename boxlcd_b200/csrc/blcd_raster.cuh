@@ -199,6 +199,37 @@ BLCD_HD uint32_t body_row(const DShape& sh, float px, float py, float s, float c
   return polygon_row(P, y, lcd_w, lcd_h, rules);
 }
 
+// Per-body raster setup, computed once per frame: integer box of a circle, or integer vertices of a polygon.  The
+// per-row functions above then only do integer / fp32 scanline work.
+struct BodyPx {
+  int kind;          // SH_CIRCLE or SH_POLY
+  int x0, y0, x1, y1;
+  PolyPx P;
+};
+
+BLCD_HD void body_px(BodyPx& o, const DShape& sh, float px, float py, float s, float c, int world_w, int lcd_w) {
+  const double ww = (double)world_w, lw = (double)lcd_w;
+  o.kind = sh.type;
+  if (sh.type == SH_CIRCLE) {
+    const double r = (double)sh.radius;
+    o.x0 = to_px((double)px - r, ww, lw); o.y0 = to_px((double)py - r, ww, lw);
+    o.x1 = to_px((double)px + r, ww, lw); o.y1 = to_px((double)py + r, ww, lw);
+    o.P.n = 0;
+  } else {
+    polygon_px(o.P, sh, px, py, s, c, ww, lw);
+    int ylo = o.P.y[0], yhi = o.P.y[0];
+    for (int i = 1; i < BLCD_MAX_VERTS; ++i)
+      if (i < o.P.n) { ylo = o.P.y[i] < ylo ? o.P.y[i] : ylo; yhi = o.P.y[i] > yhi ? o.P.y[i] : yhi; }
+    o.y0 = ylo; o.y1 = yhi; o.x0 = 0; o.x1 = 0;
+  }
+}
+
+BLCD_HD uint32_t body_px_row(const BodyPx& o, int y, int lcd_w, int lcd_h, int rules) {
+  if (y < o.y0 || y > o.y1) return 0u;   // outside the shape's rows: neither the ellipse nor the polygon rules draw anything
+  if (o.kind == SH_CIRCLE) return ellipse_row(o.x0, o.y0, o.x1, o.y1, y, lcd_w);
+  return polygon_row(o.P, y, lcd_w, lcd_h, rules);
+}
+
 BLCD_HD uint32_t row_bits_from_ink(uint32_t ink, int lcd_w) {
   uint32_t full = lcd_w >= 32 ? 0xFFFFFFFFu : ((1u << lcd_w) - 1u);
   return (~ink) & full;

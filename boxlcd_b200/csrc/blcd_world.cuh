@@ -169,6 +169,16 @@ struct Sim {
     g.n = n_worlds;
   }
 
+#if defined(BLCD_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
+  // diagnostic build: cycles per phase, accumulated into the counter words (which then no longer hold the usual counts)
+  long long ph_last;
+  BLCD_HD void ph_start() { ph_last = clock64(); }
+  BLCD_HD void ph(int i) { long long t = clock64(); cnt[i] += (uint32_t)((t - ph_last) >> 6); ph_last = t; }
+#else
+  BLCD_HD void ph_start() {}
+  BLCD_HD void ph(int) {}
+#endif
+
   // lanes that took different numbers of TOI events / position iterations wait for each other here, so that the next
   // phase runs with the whole warp instead of as two half-empty groups chasing each other through the code
   BLCD_HD void reconverge() const {
@@ -183,10 +193,12 @@ struct Sim {
   // bar_threads = 32 x (warps of this block that own at least one world); every such warp reaches every phase point the
   // same number of times (T env steps x n_substeps), so the named barrier cannot deadlock.
   int bar_threads;
-  BLCD_HD void phase_align() const {
+  BLCD_HD void phase_align(int finished_phase) {
 #ifdef __CUDA_ARCH__
     __syncwarp(live);
+    ph(finished_phase);   // (diagnostic build) work of the phase that just ended
     asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
+    ph(5);                // (diagnostic build) time spent waiting at the barrier
 #endif
   }
 
@@ -1150,7 +1162,7 @@ struct Sim {
     for (int k = 0; k < nc; ++k) contact_warm_start(k);
     for (int k = 0; k < njo; ++k) joint_init(jorder[k], jisl[k], dtRatio, h_dt);
     const int vi = sc.vel_iters;
-    if (sc.align_mode >= 1) phase_align(); else reconverge();
+    if (sc.align_mode >= 1) phase_align(0); else reconverge();   // end of: narrow phase, islands, constraint setup
     if (njo <= 3) {
       // up to three joints (every reference robot in scope) live in registers for the whole loop; contacts, whose
       // number is data dependent, stay in shared memory
@@ -1193,7 +1205,7 @@ struct Sim {
       set_hv(b, vv, ww);
     }
     // position iterations; every island stops on its own convergence
-    if (sc.align_mode >= 2) phase_align(); else reconverge();
+    if (sc.align_mode >= 2) phase_align(1); else reconverge();   // end of: velocity iterations
     uint32_t islDone = 0u;
     const uint32_t islAll = (1u << nIslands) - 1u;
     for (int it = 0; it < sc.pos_iters && islDone != islAll; ++it) {
@@ -1213,7 +1225,7 @@ struct Sim {
       islDone |= ~bad & islAll;
     }
     // write back + SynchronizeTransform
-    if (sc.align_mode >= 4) phase_align(); else reconverge();
+    if (sc.align_mode >= 4) phase_align(2); else reconverge();   // end of: position iterations
     Xf xf1[BLCD_MAX_BODIES];
     for (int b = 0; b < nb; ++b) {
       if (islandOf[b] < 0) continue;
@@ -1296,13 +1308,17 @@ struct Sim {
             sweep_advance(sb, al0);
             c0[b] = sb.c0; a0[b] = sb.a0; alpha0[b] = sb.alpha0;
           }
-          Sweep sA;
-          sA.lc = mk(0.0f, 0.0f); sA.c0 = mk(0.0f, 0.0f); sA.c = mk(0.0f, 0.0f); sA.a0 = 0.0f; sA.a = 0.0f; sA.alpha0 = walpha0[fa];
-          float t;
           ++cnt[BLCD_CNT_TOI_CALLS];
-          int state = time_of_impact(&t, sc.wall[fa], sA, bshape(b), body_sweep(b));
-          if (state == TOI_TOUCHING) alpha = fminb(al0 + (1.0f - al0) * t, 1.0f);
-          else alpha = 1.0f;
+          if (toi_cannot_touch(fa, b)) {
+            alpha = 1.0f;   // b2TimeOfImpact would come back e_separated / e_failed: same alpha, no side effects
+          } else {
+            Sweep sA;
+            sA.lc = mk(0.0f, 0.0f); sA.c0 = mk(0.0f, 0.0f); sA.c = mk(0.0f, 0.0f); sA.a0 = 0.0f; sA.a = 0.0f; sA.alpha0 = walpha0[fa];
+            float t;
+            int state = time_of_impact(&t, sc.wall[fa], sA, bshape(b), body_sweep(b));
+            if (state == TOI_TOUCHING) alpha = fminb(al0 + (1.0f - al0) * t, 1.0f);
+            else alpha = 1.0f;
+          }
           toi[p] = alpha;
           toiValid |= 1ull << p;
         }
@@ -1408,6 +1424,38 @@ struct Sim {
     }
   }
 
+  // Exact shortcut for the TOI query of body b against wall fa.  b2TimeOfImpact can only report e_touching if, at some
+  // time of the sweep, the two cores (polygon without its skin / circle centre, wall segment) come closer than
+  // target + tolerance.  Every core point p moves as c(t) + R(theta(t)) r with c and theta linear in t, so its signed
+  // distance to the wall's line stays above the smaller of its two end values minus the sag of the rotation arc,
+  // |r| dtheta^2 / 8.  If that lower bound (with 1 mm of margin for rounding) clears the threshold for every vertex, the
+  // query cannot return e_touching and its result -- alpha = 1 -- is known without running GJK and the root finder.
+  BLCD_HDN bool toi_cannot_touch(int fa, int b) const {
+    const DShape& W = sc.wall[fa];
+    const DShape& S = bshape(b);
+    V2 e = W.v[1] - W.v[0];
+    float el = len(e);
+    if (!(el > 0.0f)) return false;
+    V2 n = mk(-e.y / el, e.x / el);
+    float d0 = dot(n, W.v[0]);
+    float totalRadius = W.radius + S.radius;
+    float thresh = fmaxb(kLinearSlop, totalRadius - 3.0f * kLinearSlop) + 0.25f * kLinearSlop + 1.0e-3f;
+    Xf x0 = xf_of(c0[b], a0[b], lc_of(b));
+    const Xf& x1 = xf[b];
+    float da = a[b] - a0[b];
+    V2 lc = lc_of(b);
+    float lo = kMaxFloat, hi = -kMaxFloat, rmax = 0.0f;
+    for (int i = 0; i < S.count; ++i) {
+      float s0 = dot(n, xmul(x0, S.v[i])) - d0, s1 = dot(n, xmul(x1, S.v[i])) - d0;
+      lo = fminb(lo, fminb(s0, s1));
+      hi = fmaxb(hi, fmaxb(s0, s1));
+      rmax = fmaxb(rmax, len(S.v[i] - lc));
+    }
+    float sag = rmax * da * da * 0.125f * 1.01f;
+    // all core points on one side of the wall line for the whole sweep, and farther than the threshold
+    return (lo - sag > thresh) || (-hi - sag > thresh);
+  }
+
   BLCD_HD Sweep body_sweep(int b) const {
     Sweep s;
     s.lc = lc_of(b); s.c0 = c0[b]; s.c = c[b]; s.a0 = a0[b]; s.a = a[b]; s.alpha0 = alpha0[b];
@@ -1417,7 +1465,7 @@ struct Sim {
   // ---- b2World::Step -------------------------------------------------------------------------------------------------
   BLCD_HD void b2_step() {
     const float dt = sc.dt;
-    if (sc.align_mode >= 3) phase_align(); else reconverge();
+    if (sc.align_mode >= 3) phase_align(4); else reconverge();   // end of: TOI of the previous sub-step (+ observation)
     if (newFixture) {
       find_new_contacts((1u << (sc.nw + sc.nb)) - 1u);
       newFixture = false;
@@ -1425,7 +1473,7 @@ struct Sim {
     float dtRatio = inv_dt0 * dt;
     collide();
     solve(dt, dtRatio);
-    if (sc.align_mode >= 3) phase_align(); else reconverge();
+    if (sc.align_mode >= 3) phase_align(3); else reconverge();   // end of: write-back, sleep, broad phase
     if (!(sc.flags & BLCD_FLAG_NO_TOI)) solve_toi(dt);
     reconverge();
     inv_dt0 = 1.0f / dt;
@@ -1437,7 +1485,7 @@ struct Sim {
 
   // WorldEnv.step (world_env.py:431-452): motor speeds from the clipped action, then n_substeps world steps
   BLCD_HD void env_step(const float* action) {
-    if (sc.align_mode >= 5) phase_align();
+    if (sc.align_mode >= 5) phase_align(4);
     ep_t += 1;
     for (int j = 0; j < sc.nj; ++j) {
       const DJoint& jd = sc.joint[j];

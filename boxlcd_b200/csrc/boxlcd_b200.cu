@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
+#include <vector>
 #include "blcd_world.cuh"
 
 using namespace blcd;
@@ -76,8 +78,15 @@ __device__ __forceinline__ void write_obs(const Sim<BLOCK>& sim, const DScene& s
     }
   }
   if (o.lcd_bits || o.lcd_bool) {
+    BodyPx bp[BLCD_MAX_BODIES];   // vertex transform + fp64 metre->pixel scaling once per body, not once per row
+    for (int b = 0; b < BLCD_MAX_BODIES; ++b)
+      if (b < sc.nb) body_px(bp[b], sim.bshape(b), sim.xf[b].p.x, sim.xf[b].p.y, sim.xf[b].q.s, sim.xf[b].q.c, sc.world_w, sc.lcd_w);
     for (int R = 0; R < sc.lcd_h; ++R) {
-      uint32_t bits = sim.lcd_row(R);
+      const int y = sc.lcd_h - 1 - R;
+      uint32_t ink = 0u;
+      for (int b = 0; b < BLCD_MAX_BODIES; ++b)
+        if (b < sc.nb) ink |= body_px_row(bp[b], y, sc.lcd_w, sc.lcd_h, sc.rules);
+      uint32_t bits = row_bits_from_ink(ink, sc.lcd_w);
       if (o.lcd_bits) __stcs(o.lcd_bits + row * sc.lcd_h + R, bits);
       if (o.lcd_bool)
         for (int x = 0; x < sc.lcd_w; ++x) o.lcd_bool[(row * sc.lcd_h + R) * sc.lcd_w + x] = (uint8_t)((bits >> x) & 1u);
@@ -190,9 +199,12 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 1 : 256 / BLOCK) k_rollo
   Sim<BLOCK> sim(sc, hot_base<BLOCK>(smem_raw), state, n, w);
   sim.load(seed, world_offset + w);
   float act[BLCD_MAX_OBS];
+  sim.ph_start();
   for (int t = 0; t < T; ++t) {
     int64_t row = w * T + t;
+    sim.ph(4);
     write_obs<BLOCK>(sim, sc, out, row);   // obs_t is recorded before action t (collect.py:33-39)
+    sim.ph(6);
     sim.draw_action(act);
     if (out.actions)
       for (int k = 0; k < sc.A; ++k) __stcs(out.actions + row * sc.A + k, act[k]);
@@ -253,6 +265,7 @@ struct blcd_env {
   // pinned staging for blcd_step_host
   float* h_act = nullptr; float* h_fs = nullptr; uint32_t* h_bits = nullptr; uint8_t* h_done = nullptr;
   float* d_act = nullptr; float* d_fs = nullptr; uint32_t* d_bits = nullptr; uint8_t* d_done = nullptr;
+  std::vector<std::pair<const void*, size_t>> pinned;   // caller buffers page-locked by blcd_step_host
 };
 
 namespace {
@@ -360,6 +373,7 @@ int blcd_destroy(blcd_handle h) {
   if (h->h_bits) cudaFreeHost(h->h_bits);
   if (h->h_done) cudaFreeHost(h->h_done);
   cudaFree(h->d_act); cudaFree(h->d_fs); cudaFree(h->d_bits); cudaFree(h->d_done);
+  for (auto& r : h->pinned) cudaHostUnregister(const_cast<void*>(r.first));
   delete h;
   return 0;
 }
@@ -481,6 +495,24 @@ int blcd_rollout(blcd_handle h, int32_t T, float* full_state_dev, uint32_t* lcd_
   return 0;
 }
 
+// pin a caller-owned host buffer once (page-locks it in place) so that later copies are direct DMA transfers; returns
+// false if the driver refuses (then the call falls back to the handle's own pinned staging buffers)
+static bool pin_user_buffer(blcd_env* h, const void* p, size_t bytes) {
+  if (!p) return false;
+  for (auto& r : h->pinned)
+    if (r.first == p && r.second >= bytes) return true;
+  if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  if (h->pinned.size() >= 8) {   // keep the registry small: forget (and unpin) the oldest buffer
+    cudaHostUnregister(const_cast<void*>(h->pinned.front().first));
+    h->pinned.erase(h->pinned.begin());
+  }
+  h->pinned.emplace_back(p, bytes);
+  return true;
+}
+
 int blcd_step_host(blcd_handle h, const float* actions_host, float* full_state_host, uint32_t* lcd_bits_host, uint8_t* done_host) {
   if (!h) return fail("blcd_step_host: null handle");
   CK(cudaSetDevice(h->device));
@@ -491,19 +523,21 @@ int blcd_step_host(blcd_handle h, const float* actions_host, float* full_state_h
     CK(cudaMallocHost(&h->h_act, na)); CK(cudaMallocHost(&h->h_fs, nf)); CK(cudaMallocHost(&h->h_bits, nb)); CK(cudaMallocHost(&h->h_done, nd));
   }
   cudaStream_t st = 0;
+  const bool pa = pin_user_buffer(h, actions_host, na), pf = pin_user_buffer(h, full_state_host, nf);
+  const bool pb = pin_user_buffer(h, lcd_bits_host, nb), pd = pin_user_buffer(h, done_host, nd);
   if (actions_host) {
-    memcpy(h->h_act, actions_host, na);
-    CK(cudaMemcpyAsync(h->d_act, h->h_act, na, cudaMemcpyHostToDevice, st));
+    if (!pa) memcpy(h->h_act, actions_host, na);
+    CK(cudaMemcpyAsync(h->d_act, pa ? actions_host : h->h_act, na, cudaMemcpyHostToDevice, st));
   }
   OutPtrs out = {full_state_host ? h->d_fs : nullptr, nullptr, lcd_bits_host ? h->d_bits : nullptr, nullptr, done_host ? h->d_done : nullptr, nullptr};
   if (step_impl(h, actions_host ? h->d_act : nullptr, 1, out, st)) return -1;
-  if (full_state_host) CK(cudaMemcpyAsync(h->h_fs, h->d_fs, nf, cudaMemcpyDeviceToHost, st));
-  if (lcd_bits_host) CK(cudaMemcpyAsync(h->h_bits, h->d_bits, nb, cudaMemcpyDeviceToHost, st));
-  if (done_host) CK(cudaMemcpyAsync(h->h_done, h->d_done, nd, cudaMemcpyDeviceToHost, st));
+  if (full_state_host) CK(cudaMemcpyAsync(pf ? full_state_host : h->h_fs, h->d_fs, nf, cudaMemcpyDeviceToHost, st));
+  if (lcd_bits_host) CK(cudaMemcpyAsync(pb ? lcd_bits_host : h->h_bits, h->d_bits, nb, cudaMemcpyDeviceToHost, st));
+  if (done_host) CK(cudaMemcpyAsync(pd ? done_host : h->h_done, h->d_done, nd, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  if (full_state_host) memcpy(full_state_host, h->h_fs, nf);
-  if (lcd_bits_host) memcpy(lcd_bits_host, h->h_bits, nb);
-  if (done_host) memcpy(done_host, h->h_done, nd);
+  if (full_state_host && !pf) memcpy(full_state_host, h->h_fs, nf);
+  if (lcd_bits_host && !pb) memcpy(lcd_bits_host, h->h_bits, nb);
+  if (done_host && !pd) memcpy(done_host, h->h_done, nd);
   return 0;
 }
 

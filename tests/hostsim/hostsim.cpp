@@ -76,8 +76,15 @@ static void write_obs(const Sim<1>& sim, const DScene& sc, float* fs_out, uint32
       sim.obs_body(b, ob);
       for (int k = 0; k < 4; ++k) fs_out[sc.body[b].obs[k]] = ob[k];
     }
-  if (bits_out)
-    for (int R = 0; R < sc.lcd_h; ++R) bits_out[R] = sim.lcd_row(R);
+  if (bits_out) {
+    BodyPx bp[BLCD_MAX_BODIES];
+    for (int b = 0; b < sc.nb; ++b) body_px(bp[b], sim.bshape(b), sim.xf[b].p.x, sim.xf[b].p.y, sim.xf[b].q.s, sim.xf[b].q.c, sc.world_w, sc.lcd_w);
+    for (int R = 0; R < sc.lcd_h; ++R) {
+      uint32_t ink = 0u;
+      for (int b = 0; b < sc.nb; ++b) ink |= body_px_row(bp[b], sc.lcd_h - 1 - R, sc.lcd_w, sc.lcd_h, sc.rules);
+      bits_out[R] = row_bits_from_ink(ink, sc.lcd_w);
+    }
+  }
 }
 
 void hostsim_step(void* p, const float* actions, float* actions_out) {
