@@ -480,8 +480,8 @@ struct SepFn {  // b2SeparationFunction
   V2 localPoint, axis;
 };
 
-BLCD_HD void sepfn_init(SepFn& f, const SimplexCache& cache, const DShape& A, const Sweep& sA, const DShape& B, const Sweep& sB, float t1) {
-  Xf xfA = sweep_xf(sA, t1), xfB = sweep_xf(sB, t1);
+BLCD_HD void sepfn_init(SepFn& f, const SimplexCache& cache, const DShape& A, const Sweep& sA, const DShape& B, const Sweep& sB, float t1, bool a_static) {
+  Xf xfA = a_static ? xf_identity() : sweep_xf(sA, t1), xfB = sweep_xf(sB, t1);
   if (cache.count == 1) {
     f.type = 0;
     V2 pointA = xmul(xfA, A.v[cache.ia[0]]);
@@ -513,8 +513,8 @@ BLCD_HD void sepfn_init(SepFn& f, const SimplexCache& cache, const DShape& A, co
   }
 }
 
-BLCD_HD float sepfn_find_min(const SepFn& f, const DShape& A, const Sweep& sA, const DShape& B, const Sweep& sB, int* indexA, int* indexB, float t) {
-  Xf xfA = sweep_xf(sA, t), xfB = sweep_xf(sB, t);
+BLCD_HD float sepfn_find_min(const SepFn& f, const DShape& A, const Sweep& sA, const DShape& B, const Sweep& sB, int* indexA, int* indexB, float t, bool a_static) {
+  Xf xfA = a_static ? xf_identity() : sweep_xf(sA, t), xfB = sweep_xf(sB, t);
   if (f.type == 0) {
     V2 axisA = rmulT(xfA.q, f.axis);
     V2 axisB = rmulT(xfB.q, -f.axis);
@@ -542,8 +542,8 @@ BLCD_HD float sepfn_find_min(const SepFn& f, const DShape& A, const Sweep& sA, c
   }
 }
 
-BLCD_HD float sepfn_eval(const SepFn& f, const DShape& A, const Sweep& sA, const DShape& B, const Sweep& sB, int indexA, int indexB, float t) {
-  Xf xfA = sweep_xf(sA, t), xfB = sweep_xf(sB, t);
+BLCD_HD float sepfn_eval(const SepFn& f, const DShape& A, const Sweep& sA, const DShape& B, const Sweep& sB, int indexA, int indexB, float t, bool a_static) {
+  Xf xfA = a_static ? xf_identity() : sweep_xf(sA, t), xfB = sweep_xf(sB, t);
   if (f.type == 0) {
     V2 pointA = xmul(xfA, A.v[indexA]);
     V2 pointB = xmul(xfB, B.v[indexB]);
@@ -563,8 +563,9 @@ BLCD_HD float sepfn_eval(const SepFn& f, const DShape& A, const Sweep& sA, const
 
 enum { TOI_UNKNOWN = 0, TOI_FAILED, TOI_OVERLAPPED, TOI_TOUCHING, TOI_SEPARATED };
 
-// b2TimeOfImpact with tMax = 1.  Returns the state and writes the fraction t.
-BLCD_HDN int time_of_impact(float* t_out, const DShape& A, Sweep sA, const DShape& B, Sweep sB) {
+// b2TimeOfImpact with tMax = 1.  Returns the state and writes the fraction t.  a_static: fixture A belongs to a static
+// body at the identity transform (a wall), whose sweep evaluates to the identity exactly at every t.
+BLCD_HDN int time_of_impact(float* t_out, const DShape& A, Sweep sA, const DShape& B, Sweep sB, bool a_static) {
   const float tMax = 1.0f;
   int state = TOI_UNKNOWN;
   float t_res = tMax;
@@ -579,21 +580,21 @@ BLCD_HDN int time_of_impact(float* t_out, const DShape& A, Sweep sA, const DShap
   cache.count = 0;
   cache.metric = 0.0f;
   for (;;) {
-    Xf xfA = sweep_xf(sA, t1), xfB = sweep_xf(sB, t1);
+    Xf xfA = a_static ? xf_identity() : sweep_xf(sA, t1), xfB = sweep_xf(sB, t1);
     float distance = gjk_distance(cache, A, xfA, B, xfB);
     if (distance <= 0.0f) { state = TOI_OVERLAPPED; t_res = 0.0f; break; }
     if (distance < target + tolerance) { state = TOI_TOUCHING; t_res = t1; break; }
     SepFn fcn;
-    sepfn_init(fcn, cache, A, sA, B, sB, t1);
+    sepfn_init(fcn, cache, A, sA, B, sB, t1, a_static);
     bool done = false;
     float t2 = tMax;
     int pushBackIter = 0;
     for (;;) {
       int indexA, indexB;
-      float s2 = sepfn_find_min(fcn, A, sA, B, sB, &indexA, &indexB, t2);
+      float s2 = sepfn_find_min(fcn, A, sA, B, sB, &indexA, &indexB, t2, a_static);
       if (s2 > target + tolerance) { state = TOI_SEPARATED; t_res = tMax; done = true; break; }
       if (s2 > target - tolerance) { t1 = t2; break; }
-      float s1 = sepfn_eval(fcn, A, sA, B, sB, indexA, indexB, t1);
+      float s1 = sepfn_eval(fcn, A, sA, B, sB, indexA, indexB, t1, a_static);
       if (s1 < target - tolerance) { state = TOI_FAILED; t_res = t1; done = true; break; }
       if (s1 <= target + tolerance) { state = TOI_TOUCHING; t_res = t1; done = true; break; }
       int rootIterCount = 0;
@@ -603,7 +604,7 @@ BLCD_HDN int time_of_impact(float* t_out, const DShape& A, Sweep sA, const DShap
         if (rootIterCount & 1) t = a1 + (target - s1) * (a2 - a1) / (s2 - s1);
         else t = 0.5f * (a1 + a2);
         ++rootIterCount;
-        float s = sepfn_eval(fcn, A, sA, B, sB, indexA, indexB, t);
+        float s = sepfn_eval(fcn, A, sA, B, sB, indexA, indexB, t, a_static);
         if (absb(s - target) < tolerance) { t2 = t; break; }
         if (s > target) { a1 = t; s1 = s; }
         else { a2 = t; s2 = s; }

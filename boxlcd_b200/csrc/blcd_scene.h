@@ -25,7 +25,7 @@ constexpr uint32_t kNewFixtureBit = 1u << 16; // b2World::e_newFixture: run Find
 
 struct DShape {
   int32_t type, count;
-  float radius, _pad;
+  float radius, rmax;   // rmax: largest distance of a core vertex from the body's centre of mass (TOI pre-filter)
   V2 v[BLCD_MAX_VERTS];
   V2 n[BLCD_MAX_VERTS];
   V2 centroid;
@@ -72,6 +72,8 @@ struct DScene {
   int32_t h_vel, h_pos, h_mass, h_joint, h_con, hot_words;
   DShape wall[BLCD_MAX_WALLS];
   Box wallFat[BLCD_MAX_WALLS];
+  V2 wall_n[BLCD_MAX_WALLS];      // unit normal of the wall's line and its offset (n . x = d), for the TOI pre-filter
+  float wall_d[BLCD_MAX_WALLS];
   DBody body[BLCD_MAX_BODIES];
   DJoint joint[BLCD_MAX_JOINTS];
   DPair pair[kMaxPairs];
@@ -229,6 +231,10 @@ inline const char* build_scene(DScene& sc, const blcd_spec& sp, int maxm) {
     V2 r = mk(kPolygonRadius, kPolygonRadius), e = mk(kAabbExtension, kAabbExtension);
     sc.wallFat[i].lo = (lo - r) - e;
     sc.wallFat[i].hi = (hi + r) + e;
+    V2 ed = b - a;
+    float el = len(ed);
+    sc.wall_n[i] = el > 0.0f ? mk(-ed.y / el, ed.x / el) : mk(0.0f, 0.0f);
+    sc.wall_d[i] = dot(sc.wall_n[i], a);
   }
   for (int b = 0; b < sc.nb; ++b) {
     const blcd_body_def& bd = sp.bodies[b];
@@ -237,6 +243,8 @@ inline const char* build_scene(DScene& sc, const blcd_spec& sp, int maxm) {
     for (int k = 0; k < d.nvar; ++k) {
       make_shape(d.shape[k], bd.shape[k]);
       mass_of(d.shape[k], f32(bd.density), &d.invMass[k], &d.invI[k], &d.lc[k]);
+      d.shape[k].rmax = 0.0f;
+      for (int i = 0; i < d.shape[k].count; ++i) d.shape[k].rmax = fmaxb(d.shape[k].rmax, len(d.shape[k].v[i] - d.lc[k]));
     }
     if (d.nvar == 1) { d.shape[1] = d.shape[0]; d.invMass[1] = d.invMass[0]; d.invI[1] = d.invI[0]; d.lc[1] = d.lc[0]; }
     d.friction = f32(bd.friction); d.restitution = f32(bd.restitution);

@@ -1284,46 +1284,60 @@ struct Sim {
     for (int b = 0; b < nb; ++b) alpha0[b] = 0.0f;
     for (int i = 0; i < BLCD_MAX_WALLS; ++i) walpha0[i] = 0.0f;
     for (int k = 0; k < ncl; ++k) { toiCount[clist[k]] = 0; toi[clist[k]] = 1.0f; }
+    uint32_t toiMask[BLCD_MAX_BODIES];
+    for (int b = 0; b < BLCD_MAX_BODIES; ++b)
+      if (b < nb) toiMask[b] = is_awake(b) ? toi_prefilter(b) : 0xFFFFFFFFu;
     for (;;) {
+      // Pass 1, in contact-list order: bookkeeping of b2World::SolveTOI's scan (sweeps onto a common interval, counters)
+      // and collection of the pairs that really need a time-of-impact query.  The queries are pure functions of the
+      // sweeps, so they are deferred to pass 2, where all lanes of the warp run theirs together instead of each lane
+      // hitting the long GJK / root-finder code at a different list position.  If a body's sweep is about to be advanced
+      // while queries on it are pending, those are flushed first, so every query still sees exactly Box2D's inputs.
+      uint8_t pend[16];
+      float pend_al0[16];   // common interval start of each pending query, as of its place in the list
+      int npend = 0;
+      for (int k = 0; k < ncl; ++k) {
+        int p = clist[k];
+        if (!((enabled >> p) & 1ull)) continue;
+        if (toiCount[p] > kMaxSubSteps) continue;
+        if ((toiValid >> p) & 1ull) continue;
+        int fa = sc.pair[p].fa, fb = sc.pair[p].fb;
+        if (fa >= nw) continue;          // two non-bullet dynamic bodies
+        int b = fb - nw;
+        if (!is_awake(b)) continue;      // neither side active
+        // put both sweeps on the same interval
+        if (walpha0[fa] < alpha0[b]) walpha0[fa] = alpha0[b];
+        else if (alpha0[b] < walpha0[fa]) {
+          toi_flush(pend, pend_al0, npend, toi, toiValid);
+          Sweep sb = body_sweep(b);
+          sweep_advance(sb, walpha0[fa]);
+          c0[b] = sb.c0; a0[b] = sb.a0; alpha0[b] = sb.alpha0;
+          toiMask[b] = toi_prefilter(b);   // the sweep's start moved
+        }
+        ++cnt[BLCD_CNT_TOI_CALLS];
+        if (!((toiMask[b] >> fa) & 1u)) {
+          toi[p] = 1.0f;   // b2TimeOfImpact would come back e_separated / e_failed: alpha = 1, no side effects
+          toiValid |= 1ull << p;
+        } else {
+          if (npend == 16) toi_flush(pend, pend_al0, npend, toi, toiValid);
+          pend_al0[npend] = walpha0[fa];
+          pend[npend++] = (uint8_t)p;
+        }
+      }
+      // Pass 2: the deferred queries
+      toi_flush(pend, pend_al0, npend, toi, toiValid);
+      // Pass 3: earliest time of impact, first in list order on ties
       int minPair = -1;
       float minAlpha = 1.0f;
       for (int k = 0; k < ncl; ++k) {
         int p = clist[k];
         if (!((enabled >> p) & 1ull)) continue;
         if (toiCount[p] > kMaxSubSteps) continue;
-        float alpha = 1.0f;
-        if ((toiValid >> p) & 1ull) {
-          alpha = toi[p];
-        } else {
-          int fa = sc.pair[p].fa, fb = sc.pair[p].fb;
-          if (fa >= nw) continue;          // two non-bullet dynamic bodies
-          int b = fb - nw;
-          if (!is_awake(b)) continue;      // neither side active
-          // put both sweeps on the same interval
-          float al0 = walpha0[fa];
-          if (walpha0[fa] < alpha0[b]) { al0 = alpha0[b]; walpha0[fa] = al0; }
-          else if (alpha0[b] < walpha0[fa]) {
-            al0 = walpha0[fa];
-            Sweep sb = body_sweep(b);
-            sweep_advance(sb, al0);
-            c0[b] = sb.c0; a0[b] = sb.a0; alpha0[b] = sb.alpha0;
-          }
-          ++cnt[BLCD_CNT_TOI_CALLS];
-          if (toi_cannot_touch(fa, b)) {
-            alpha = 1.0f;   // b2TimeOfImpact would come back e_separated / e_failed: same alpha, no side effects
-          } else {
-            Sweep sA;
-            sA.lc = mk(0.0f, 0.0f); sA.c0 = mk(0.0f, 0.0f); sA.c = mk(0.0f, 0.0f); sA.a0 = 0.0f; sA.a = 0.0f; sA.alpha0 = walpha0[fa];
-            float t;
-            int state = time_of_impact(&t, sc.wall[fa], sA, bshape(b), body_sweep(b));
-            if (state == TOI_TOUCHING) alpha = fminb(al0 + (1.0f - al0) * t, 1.0f);
-            else alpha = 1.0f;
-          }
-          toi[p] = alpha;
-          toiValid |= 1ull << p;
-        }
+        if (!((toiValid >> p) & 1ull)) continue;
+        float alpha = toi[p];
         if (alpha < minAlpha) { minPair = p; minAlpha = alpha; }
       }
+      ph(4);   // (diagnostic build) candidate scan: skip tests + time-of-impact queries
       if (minPair < 0 || 1.0f - 10.0f * kEps < minAlpha) break;
       const int wl = sc.pair[minPair].fa, b = sc.pair[minPair].fb - nw;
       // advance both bodies to the time of impact
@@ -1418,42 +1432,64 @@ struct Sim {
         if (sc.pair[p].fb == nw + b || sc.pair[p].fa == nw + b) toiValid &= ~(1ull << p);
       }
       int ncl0 = ncl;
+      toiMask[b] = toi_prefilter(b);   // new sweep after the event
+      ph(3);   // (diagnostic build) TOI event: advance, mini-island solve
       find_new_contacts(moved);
       for (int k = 0; k < ncl - ncl0; ++k) { toiCount[clist[k]] = 0; toi[clist[k]] = 1.0f; toiValid &= ~(1ull << clist[k]); enabled |= 1ull << clist[k]; }
       moved = 0u;
     }
   }
 
-  // Exact shortcut for the TOI query of body b against wall fa.  b2TimeOfImpact can only report e_touching if, at some
-  // time of the sweep, the two cores (polygon without its skin / circle centre, wall segment) come closer than
-  // target + tolerance.  Every core point p moves as c(t) + R(theta(t)) r with c and theta linear in t, so its signed
-  // distance to the wall's line stays above the smaller of its two end values minus the sag of the rotation arc,
-  // |r| dtheta^2 / 8.  If that lower bound (with 1 mm of margin for rounding) clears the threshold for every vertex, the
-  // query cannot return e_touching and its result -- alpha = 1 -- is known without running GJK and the root finder.
-  BLCD_HDN bool toi_cannot_touch(int fa, int b) const {
-    const DShape& W = sc.wall[fa];
+  // Exact pre-filter for the TOI queries of body b: bit k of the result is set if b2TimeOfImpact against wall k could
+  // report e_touching.  It can only do so if, at some time of the sweep, the two cores (polygon without its skin / circle
+  // centre, wall segment) come closer than target + tolerance.  Every core point moves as c(t) + R(theta(t)) r with c and
+  // theta linear in t, so its signed distance to the wall's line stays above the smaller of its two end values minus the
+  // sag of the rotation arc, |r| dtheta^2 / 8.  If that lower bound (with 1 mm of margin for rounding) clears the
+  // threshold for every vertex, the query's answer -- alpha = 1 -- is known without running GJK and the root finder.
+  // Evaluated once per body (all lanes together) instead of once per candidate pair.
+  BLCD_HDN uint32_t toi_prefilter(int b) const {
     const DShape& S = bshape(b);
-    V2 e = W.v[1] - W.v[0];
-    float el = len(e);
-    if (!(el > 0.0f)) return false;
-    V2 n = mk(-e.y / el, e.x / el);
-    float d0 = dot(n, W.v[0]);
-    float totalRadius = W.radius + S.radius;
-    float thresh = fmaxb(kLinearSlop, totalRadius - 3.0f * kLinearSlop) + 0.25f * kLinearSlop + 1.0e-3f;
     Xf x0 = xf_of(c0[b], a0[b], lc_of(b));
     const Xf& x1 = xf[b];
     float da = a[b] - a0[b];
-    V2 lc = lc_of(b);
-    float lo = kMaxFloat, hi = -kMaxFloat, rmax = 0.0f;
-    for (int i = 0; i < S.count; ++i) {
-      float s0 = dot(n, xmul(x0, S.v[i])) - d0, s1 = dot(n, xmul(x1, S.v[i])) - d0;
-      lo = fminb(lo, fminb(s0, s1));
-      hi = fmaxb(hi, fmaxb(s0, s1));
-      rmax = fmaxb(rmax, len(S.v[i] - lc));
+    float sag = S.rmax * da * da * 0.125f * 1.01f;
+    V2 p0[BLCD_MAX_VERTS], p1[BLCD_MAX_VERTS];
+    for (int i = 0; i < BLCD_MAX_VERTS; ++i)
+      if (i < S.count) { p0[i] = xmul(x0, S.v[i]); p1[i] = xmul(x1, S.v[i]); }
+    uint32_t mask = 0u;
+    for (int k = 0; k < sc.nw; ++k) {
+      V2 n = sc.wall_n[k];
+      float d0 = sc.wall_d[k];
+      float totalRadius = sc.wall[k].radius + S.radius;
+      float thresh = fmaxb(kLinearSlop, totalRadius - 3.0f * kLinearSlop) + 0.25f * kLinearSlop + 1.0e-3f;
+      float lo = kMaxFloat, hi = -kMaxFloat;
+      for (int i = 0; i < BLCD_MAX_VERTS; ++i) {
+        if (i < S.count) {
+          float s0 = dot(n, p0[i]) - d0, s1 = dot(n, p1[i]) - d0;
+          lo = fminb(lo, fminb(s0, s1));
+          hi = fmaxb(hi, fmaxb(s0, s1));
+        }
+      }
+      bool clear = (lo - sag > thresh) || (-hi - sag > thresh);   // one side of the line for the whole sweep, far enough
+      if (!clear || !(dot(n, n) > 0.5f)) mask |= 1u << k;
     }
-    float sag = rmax * da * da * 0.125f * 1.01f;
-    // all core points on one side of the wall line for the whole sweep, and farther than the threshold
-    return (lo - sag > thresh) || (-hi - sag > thresh);
+    return mask;
+  }
+
+  // run the pending time-of-impact queries (pairs wall fa x body b) against the current sweeps
+  BLCD_HD void toi_flush(const uint8_t* pend, const float* pend_al0, int& npend, float* toi, uint64_t& toiValid) {
+    for (int j = 0; j < npend; ++j) {
+      int p = pend[j];
+      int fa = sc.pair[p].fa, b = sc.pair[p].fb - sc.nw;
+      float al0 = pend_al0[j];   // == alpha0[b]: a body's own sweep is never advanced while it has queries pending
+      Sweep sA;
+      sA.lc = mk(0.0f, 0.0f); sA.c0 = mk(0.0f, 0.0f); sA.c = mk(0.0f, 0.0f); sA.a0 = 0.0f; sA.a = 0.0f; sA.alpha0 = al0;
+      float t;
+      int state = time_of_impact(&t, sc.wall[fa], sA, bshape(b), body_sweep(b), true);
+      toi[p] = state == TOI_TOUCHING ? fminb(al0 + (1.0f - al0) * t, 1.0f) : 1.0f;
+      toiValid |= 1ull << p;
+    }
+    npend = 0;
   }
 
   BLCD_HD Sweep body_sweep(int b) const {
