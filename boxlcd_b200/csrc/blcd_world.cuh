@@ -196,9 +196,15 @@ struct Sim {
   BLCD_HD void phase_align(int finished_phase) {
 #ifdef __CUDA_ARCH__
     __syncwarp(live);
+#if defined(BLCD_PHASE_CLOCKS) && BLCD_PHASE_CLOCKS == 2
+    ph(7);                // (diagnostic build 2) work is dumped, the WAIT is attributed to the phase that just ended
+    asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
+    ph(finished_phase);
+#else
     ph(finished_phase);   // (diagnostic build) work of the phase that just ended
     asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
     ph(5);                // (diagnostic build) time spent waiting at the barrier
+#endif
 #endif
   }
 
