@@ -249,6 +249,27 @@ def main():
            'd2h_bytes_per_step': int(h_fs.nbytes + h_bits.nbytes + h_done.nbytes), 'worlds': ne, 'env_steps_timed': Te,
            'api': 'blcd_step_host: host actions in, host full_state + packed frames + done out, one call per env step'}
 
+  # ---- the rasterizer alone (blcd_render_poses): frames/s and HBM GB/s from poses resident in HBM -------------------------
+  render = None
+  if rank == 0:
+    nr = 4 * 1024 * 1024
+    poses, _ = v.get_poses_dev()
+    poses = poses[torch.randint(0, n, (nr,), device=dev)].contiguous()
+    out_bits = torch.empty((nr, v.H), dtype=torch.int32, device=dev)
+    for _ in range(3):
+      v.render_poses_dev(poses)
+    torch.cuda.synchronize()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for _ in range(5):
+      v.render_poses_dev(poses)
+    r1.record()
+    torch.cuda.synchronize()
+    r_ms = r0.elapsed_time(r1) / 5
+    r_bytes = nr * (16 * v.B + 4 * v.H)
+    render = {'kernel': 'k_render_poses', 'frames': nr, 'ms': r_ms, 'frames_per_s': nr / (r_ms / 1e3), 'algorithmic_bytes_per_frame': 16 * v.B + 4 * v.H,
+              'achieved_gbs': r_bytes / (r_ms / 1e3) / 1e9}
+    del poses, out_bits
   if rank != 0:
     if world_size > 1:
       dist.destroy_process_group()
@@ -282,6 +303,7 @@ def main():
                  'solver': 'Box2D 2.3 semantics: 3 sub-steps x (180 velocity + <=60 position iterations), TOI vs walls, sleeping',
                  'manifold_slot_overflows': overflow},
       'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu,
+      'render_roofline': None if render is None else dict(render, bound='hbm', peak=peak_gbs, unit='GB/s', frac=render['achieved_gbs'] / peak_gbs),
   }
   print(json.dumps(line), flush=True)
   if world_size > 1:

@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, 'csrc')
 _lib = None
 
 SYMBOLS = ['blcd_last_error', 'blcd_version', 'blcd_create', 'blcd_destroy', 'blcd_reset', 'blcd_step', 'blcd_step_observe', 'blcd_observe',
-           'blcd_rollout', 'blcd_step_host', 'blcd_render_poses', 'blcd_render_poses_sized', 'blcd_set_bodies', 'blcd_get_bodies', 'blcd_get_poses',
+           'blcd_rollout', 'blcd_step_host', 'blcd_render_poses', 'blcd_render_poses_sized', 'blcd_set_bodies', 'blcd_get_bodies', 'blcd_get_poses', 'blcd_check_finite',
            'blcd_state_bytes', 'blcd_save_state', 'blcd_load_state', 'blcd_num_worlds', 'blcd_kernel_launches', 'blcd_last_step_ms',
            'blcd_enable_timing', 'blcd_get_counters', 'blcd_scene_info']
 
@@ -47,6 +47,7 @@ def lib():
   l.blcd_set_bodies.argtypes = [vp, vp, vp, u64]
   l.blcd_get_bodies.argtypes = [vp, vp, u64]
   l.blcd_get_poses.argtypes = [vp, vp, vp, u64]
+  l.blcd_check_finite.argtypes = [vp, vp, C.POINTER(i64)]
   l.blcd_state_bytes.argtypes = [vp]
   l.blcd_state_bytes.restype = i64
   l.blcd_save_state.argtypes = [vp, vp, u64]

@@ -136,31 +136,33 @@ BLCD_HD uint32_t polygon_row(const PolyPx& P, int y, int w, int h, int rules) {
     mask |= span_mask(xs, xe, w);
     pos = xe + 1; have_pos = true;
   }
-  // apex extension: two sloped edges of the same direction meeting in an integer vertex on this row
-  for (int i = 0; i < ne; ++i) {
+  // apex extension: two sloped edges of the same direction meeting in an integer vertex on this row.  Integer tests come
+  // first so that the (fp32) slopes are only divided out for edge pairs that really meet on this row.
+  for (int i = 1; i < ne; ++i) {
     int ij = i + 1 < n ? i + 1 : 0;
     int cx0 = P.x[i], cy0 = P.y[i], cx1 = P.x[ij], cy1 = P.y[ij];
-    if (cy0 == cy1) continue;
-    float cdx = (float)(cx1 - cx0) / (float)(cy1 - cy0);
-    if (cdx == 0.0f) continue;
+    if (cy0 == cy1 || cx0 == cx1) continue;                 // horizontal, or slope exactly 0
     int cmin = cy0 < cy1 ? cy0 : cy1, cmax = cy0 < cy1 ? cy1 : cy0;
     if (y != cmin && y != cmax) continue;
+    int vx = (cy0 == y) ? cx0 : cx1;
+    const bool cpos = ((cx1 - cx0) > 0) == ((cy1 - cy0) > 0);  // sign of dx = (x1 - x0) / (y1 - y0)
     for (int k = 0; k < i; ++k) {
       int kj = k + 1 < n ? k + 1 : 0;
       int ox0 = P.x[k], oy0 = P.y[k], ox1 = P.x[kj], oy1 = P.y[kj];
-      if (oy0 == oy1) continue;
-      float odx = (float)(ox1 - ox0) / (float)(oy1 - oy0);
-      if (odx == 0.0f || (cdx > 0.0f) != (odx > 0.0f)) continue;
+      if (oy0 == oy1 || ox0 == ox1) continue;
+      const bool opos = ((ox1 - ox0) > 0) == ((oy1 - oy0) > 0);
+      if (cpos != opos) continue;
       int omin = oy0 < oy1 ? oy0 : oy1, omax = oy0 < oy1 ? oy1 : oy0;
       bool top = (y == cmin && y == omin);
       bool bot = (y == cmax && y == omax && y == Ymax);
       if (!top && !bot) continue;
-      int vx = (cy0 == y) ? cx0 : cx1;
       int ovx = (oy0 == y) ? ox0 : ox1;
       if (vx != ovx) continue;
+      float cdx = (float)(cx1 - cx0) / (float)(cy1 - cy0);
+      float odx = (float)(ox1 - ox0) / (float)(oy1 - oy0);
       int y2 = (y == Ymax) ? y - 1 : y + 1;
       float a1 = edge_x_at(cx0, cy0, cdx, y2), a2 = edge_x_at(ox0, oy0, odx, y2);
-      if ((bot && cdx > 0.0f) || (top && cdx < 0.0f)) {
+      if ((bot && cpos) || (top && !cpos)) {
         int s = round_up_px(BLCD_FADD(a1 > a2 ? a1 : a2, 1.0f));
         if (s <= vx) mask |= span_mask(s, vx, w);
       } else {

@@ -151,6 +151,19 @@ __global__ void k_get_bodies(const DScene* scene_g, const uint32_t* state, int64
   }
 }
 
+// failure detection: worlds whose body state stopped being finite (a diverged solve); flags[w] = 1 for those
+__global__ void k_check_finite(const DScene* scene_g, const uint32_t* state, int64_t n, uint8_t* flags, unsigned long long* count) {
+  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n) return;
+  const DScene& sc = *scene_g;
+  const float* sf = reinterpret_cast<const float*>(state);
+  bool ok = true;
+  for (int b = 0; b < sc.nb; ++b)
+    for (int k = 0; k < 6; ++k) ok = ok && isfinite(sf[(int64_t)(kBodyWords * b + k) * n + w]);
+  if (flags) flags[w] = ok ? 0 : 1;
+  if (!ok) atomicAdd(count, 1ull);
+}
+
 // b2Transform of every dynamic body exactly as the simulation holds it (position, sincosf(angle)): what lcd_render consumes
 __global__ void k_get_poses(const DScene* scene_g, const uint32_t* state, int64_t n, float* poses, uint32_t* variants) {
   int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -224,29 +237,69 @@ __global__ void __launch_bounds__(BLOCK) k_observe(const DScene* scene_g, uint32
   write_obs<BLOCK>(sim, sc, out, w);
 }
 
-// one thread per (world, frame row): lanes 0..H-1 of consecutive worlds write consecutive words -> coalesced stores
-__global__ void __launch_bounds__(256) k_render_poses(const DScene* scene_g, const float* poses, const uint32_t* variants, int64_t n,
-                                                       int lcd_w, int lcd_h, uint32_t* bits) {
-  __shared__ DScene sc_s;
+// lcd_render from poses.  One thread per (frame, row): lanes 0..H-1 of consecutive frames write consecutive words, so the
+// stores are fully coalesced and need no atomics.  The H lanes of a frame first share the per-frame set-up through shared
+// memory -- each vertex is transformed (fp32, no FMA) and scaled to pixels (fp64, truncation) ONCE per frame by one lane
+// instead of once per row -- then every lane scans its own row over all bodies.
+constexpr int kRenderThreads = 256;
+__global__ void __launch_bounds__(kRenderThreads) k_render_poses(const DScene* scene_g, const float* poses, const uint32_t* variants, int64_t n,
+                                                                  int lcd_w, int lcd_h, uint32_t* bits) {
+  extern __shared__ __align__(16) unsigned char rsm[];
+  DScene* scp = reinterpret_cast<DScene*>(rsm);
+  BodyPx* bp_all = reinterpret_cast<BodyPx*>(rsm + kSceneBytes);
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(scene_g);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&sc_s);
-    for (int i = threadIdx.x; i < (int)(sizeof(DScene) / 4); i += blockDim.x) dst[i] = src[i];
+    uint32_t* dst = reinterpret_cast<uint32_t*>(scp);
+    for (int i = threadIdx.x; i < (int)(sizeof(DScene) / 4); i += kRenderThreads) dst[i] = src[i];
     __syncthreads();
   }
-  const DScene& sc = sc_s;
-  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= n * lcd_h) return;
-  int64_t w = gid / lcd_h;
-  int R = (int)(gid - w * lcd_h);
-  int y = lcd_h - 1 - R;
-  uint32_t variant = variants ? variants[w] : 0u;
-  uint32_t ink = 0u;
-  for (int b = 0; b < sc.nb; ++b) {
-    const float* p = poses + (w * sc.nb + b) * 4;
-    ink |= body_row(sc.body[b].shape[(variant >> b) & 1u], p[0], p[1], p[2], p[3], y, sc.world_w, lcd_w, lcd_h, sc.rules);
+  const DScene& sc = *scp;
+  const int fpb = kRenderThreads / lcd_h;                 // frames per block
+  const int f = threadIdx.x / lcd_h, R = threadIdx.x - f * lcd_h;
+  const int64_t w = (int64_t)blockIdx.x * fpb + f;
+  const bool live = f < fpb && w < n;
+  BodyPx* bp = bp_all + f * BLCD_MAX_BODIES;
+  const uint32_t variant = (live && variants) ? variants[w] : 0u;
+  if (live) {
+    const double ww = (double)sc.world_w, lw = (double)lcd_w;
+    for (int item = R; item < sc.nb * BLCD_MAX_VERTS; item += lcd_h) {
+      const int b = item / BLCD_MAX_VERTS, vi = item - b * BLCD_MAX_VERTS;
+      const DShape& sh = sc.body[b].shape[(variant >> b) & 1u];
+      const float* p = poses + (w * sc.nb + b) * 4;
+      if (sh.type == SH_CIRCLE) {
+        if (vi == 0) {
+          const double r = (double)sh.radius;
+          bp[b].kind = SH_CIRCLE;
+          bp[b].x0 = to_px((double)p[0] - r, ww, lw); bp[b].y0 = to_px((double)p[1] - r, ww, lw);
+          bp[b].x1 = to_px((double)p[0] + r, ww, lw); bp[b].y1 = to_px((double)p[1] + r, ww, lw);
+          bp[b].P.n = 0;
+        }
+      } else if (vi < sh.count) {
+        const float px = p[0], py = p[1], sn = p[2], cs = p[3], vx = sh.v[vi].x, vy = sh.v[vi].y;
+        float wx = BLCD_FADD(BLCD_FSUB(BLCD_FMUL(cs, vx), BLCD_FMUL(sn, vy)), px);
+        float wy = BLCD_FADD(BLCD_FADD(BLCD_FMUL(sn, vx), BLCD_FMUL(cs, vy)), py);
+        bp[b].P.x[vi] = to_px((double)wx, ww, lw);
+        bp[b].P.y[vi] = to_px((double)wy, ww, lw);
+        if (vi == 0) { bp[b].kind = SH_POLY; bp[b].P.n = sh.count; }
+      }
+    }
   }
-  bits[gid] = row_bits_from_ink(ink, lcd_w);
+  __syncthreads();
+  if (live) {
+    for (int b = R; b < sc.nb; b += lcd_h) {               // row bounds of each polygon, one lane per body
+      if (bp[b].kind != SH_CIRCLE) {
+        int ylo = bp[b].P.y[0], yhi = bp[b].P.y[0];
+        for (int i = 1; i < bp[b].P.n; ++i) { ylo = min(ylo, bp[b].P.y[i]); yhi = max(yhi, bp[b].P.y[i]); }
+        bp[b].y0 = ylo; bp[b].y1 = yhi;
+      }
+    }
+  }
+  __syncthreads();
+  if (!live) return;
+  const int y = lcd_h - 1 - R;
+  uint32_t ink = 0u;
+  for (int b = 0; b < sc.nb; ++b) ink |= body_px_row(bp[b], y, lcd_w, lcd_h, sc.rules);
+  bits[w * lcd_h + R] = row_bits_from_ink(ink, lcd_w);
 }
 
 }  // namespace
@@ -259,7 +312,7 @@ struct blcd_env {
   uint64_t seed = 0;
   int device = 0, block = 64;
   int64_t launches = 0;
-  bool timing = false;
+  bool timing = false, render_attr_set = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   float last_ms = -1.0f;
   // pinned staging for blcd_step_host
@@ -421,6 +474,23 @@ int blcd_get_bodies(blcd_handle h, float* bodies_dev, uint64_t stream) {
   return 0;
 }
 
+int blcd_check_finite(blcd_handle h, uint8_t* invalid_dev, int64_t* n_invalid_host) {
+  if (!h || !n_invalid_host) return fail("blcd_check_finite: bad arguments");
+  CK(cudaSetDevice(h->device));
+  unsigned long long* cnt = nullptr;
+  CK(cudaMalloc(&cnt, sizeof(unsigned long long)));
+  CK(cudaMemset(cnt, 0, sizeof(unsigned long long)));
+  k_check_finite<<<(unsigned)((h->n + 255) / 256), 256>>>(h->scene_dev, h->state, h->n, invalid_dev, cnt);
+  cudaError_t e = cudaGetLastError();
+  unsigned long long host = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&host, cnt, sizeof(host), cudaMemcpyDeviceToHost);
+  cudaFree(cnt);
+  if (e != cudaSuccess) return fail(std::string("blcd_check_finite: ") + cudaGetErrorString(e));
+  *n_invalid_host = (int64_t)host;
+  h->launches += 1;
+  return 0;
+}
+
 int blcd_get_poses(blcd_handle h, float* poses_dev, uint32_t* variant_dev, uint64_t stream) {
   if (!h || !poses_dev) return fail("blcd_get_poses: bad arguments");
   CK(cudaSetDevice(h->device));
@@ -554,9 +624,15 @@ int blcd_render_poses_sized(blcd_handle h, const float* poses_dev, const uint32_
   if (lcd_w > 32) return fail("blcd_render_poses: frame width > 32 needs the tiled path (not built)");
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  int64_t total = n * lcd_h;
+  if (lcd_h > kRenderThreads) return fail("blcd_render_poses: frame height out of range");
+  const int fpb = kRenderThreads / lcd_h;
+  const size_t rsm_bytes = (size_t)kSceneBytes + sizeof(BodyPx) * BLCD_MAX_BODIES * (size_t)fpb;
+  if (!h->render_attr_set) {
+    CK(cudaFuncSetAttribute(k_render_poses, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kSceneBytes + sizeof(BodyPx) * BLCD_MAX_BODIES * kRenderThreads)));
+    h->render_attr_set = true;
+  }
   if (begin_timing(h, st)) return -1;
-  k_render_poses<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(h->scene_dev, poses_dev, variant_dev, n, lcd_w, lcd_h, lcd_bits_dev);
+  k_render_poses<<<(unsigned)((n + fpb - 1) / fpb), kRenderThreads, rsm_bytes, st>>>(h->scene_dev, poses_dev, variant_dev, n, lcd_w, lcd_h, lcd_bits_dev);
   CK(cudaGetLastError());
   if (end_timing(h, st)) return -1;
   h->launches += 1;

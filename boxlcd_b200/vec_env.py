@@ -121,6 +121,16 @@ class VecWorldEnv:
     _lib.check(self.l.blcd_get_poses(self.h, _ptr(poses), _ptr(variants), self._stream()))
     return poses, variants
 
+  def check_finite(self, auto_reset=False):
+    """failure detection: (number of worlds whose state went non-finite, uint8 flag tensor); optionally reset them"""
+    flags = torch.zeros((self.n,), dtype=torch.uint8, device=self.device)
+    cnt = C.c_int64()
+    torch.cuda.current_stream(self.device).synchronize()
+    _lib.check(self.l.blcd_check_finite(self.h, _ptr(flags), C.byref(cnt)))
+    if auto_reset and cnt.value:
+      self.reset_dev(torch.nonzero(flags).flatten().to(torch.int64))
+    return int(cnt.value), flags
+
   def counters(self):
     out = torch.empty((self.n, 8), dtype=torch.int32, device=self.device)
     _lib.check(self.l.blcd_get_counters(self.h, _ptr(out), self._stream()))

@@ -171,6 +171,10 @@ int64_t blcd_state_bytes(blcd_handle h);
 int blcd_save_state(blcd_handle h, void* buf_dev, uint64_t stream);
 int blcd_load_state(blcd_handle h, const void* buf_dev, uint64_t stream);
 
+/* Failure detection: counts the worlds whose body state is no longer finite (NaN / inf after a diverged solve) and, if
+ * invalid_dev != NULL ([N] uint8), flags them; the caller decides whether to blcd_reset those indices.  Synchronous. */
+int blcd_check_finite(blcd_handle h, uint8_t* invalid_dev, int64_t* n_invalid_host);
+
 /* Introspection used by tests and bench.py */
 int64_t blcd_num_worlds(blcd_handle h);
 int64_t blcd_kernel_launches(blcd_handle h);   /* number of kernels this handle has launched so far */

@@ -180,3 +180,18 @@ def test_object2_random_shapes_render_and_step():
   assert (og['lcd'] == oracle.unpack_bits(oo['lcd_bits'], 16)).all((1, 2)).mean() > 0.999
   v.rollout_dev(20); ow.rollout(20, want=())
   assert np.isfinite(v.get_bodies()).all()
+
+
+def test_failure_detection_flags_and_resets_non_finite_worlds():
+  env = make_env('Bounce2')
+  v = vec(env, 64, seed=2)
+  v.reset_dev()
+  assert v.check_finite()[0] == 0
+  b = v.get_bodies()
+  b[5, 0, 0] = np.nan
+  b[9, 1, 4] = np.inf
+  v.set_bodies(b)
+  n_bad, flags = v.check_finite()
+  assert n_bad == 2 and flags.cpu().numpy().nonzero()[0].tolist() == [5, 9]
+  v.check_finite(auto_reset=True)
+  assert v.check_finite()[0] == 0 and np.isfinite(v.get_bodies()).all()
