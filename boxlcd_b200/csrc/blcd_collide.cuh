@@ -123,14 +123,62 @@ BLCD_HD float find_max_separation(int* edgeIndex, const DShape& p1, const Xf& xf
   return maxSep;
 }
 
+// Box2D 2.3.0's b2EdgeSeparation / hill-climbing b2FindMaxSeparation (the brute-force loop above is 2.3.1's).  Selected
+// together with the 2.3.0 reference-face hysteresis by BLCD_FLAG_REFFACE_2_3_0: the reference's recorded Object2-cubes
+// episode is reproduced with these rules, i.e. this is what pybox2d 2.3.10 vendors.
+BLCD_HD float edge_separation_230(const DShape& p1, const Xf& xf1, int edge1, const DShape& p2, const Xf& xf2) {
+  V2 normal1World = rmul(xf1.q, p1.n[edge1]);
+  V2 normal1 = rmulT(xf2.q, normal1World);
+  int index = 0;
+  float minDot = kMaxFloat;
+  for (int i = 0; i < p2.count; ++i) {
+    float d = dot(p2.v[i], normal1);
+    if (d < minDot) { minDot = d; index = i; }
+  }
+  V2 v1 = xmul(xf1, p1.v[edge1]);
+  V2 v2 = xmul(xf2, p2.v[index]);
+  return dot(v2 - v1, normal1World);
+}
+
+BLCD_HD float find_max_separation_230(int* edgeIndex, const DShape& p1, const Xf& xf1, const DShape& p2, const Xf& xf2) {
+  int count1 = p1.count;
+  V2 d = xmul(xf2, p2.centroid) - xmul(xf1, p1.centroid);
+  V2 dLocal1 = rmulT(xf1.q, d);
+  int edge = 0;
+  float maxDot = -kMaxFloat;
+  for (int i = 0; i < count1; ++i) {
+    float dt = dot(p1.n[i], dLocal1);
+    if (dt > maxDot) { maxDot = dt; edge = i; }
+  }
+  float s = edge_separation_230(p1, xf1, edge, p2, xf2);
+  int prevEdge = edge - 1 >= 0 ? edge - 1 : count1 - 1;
+  float sPrev = edge_separation_230(p1, xf1, prevEdge, p2, xf2);
+  int nextEdge = edge + 1 < count1 ? edge + 1 : 0;
+  float sNext = edge_separation_230(p1, xf1, nextEdge, p2, xf2);
+  int bestEdge, increment;
+  float bestSeparation;
+  if (sPrev > s && sPrev > sNext) { increment = -1; bestEdge = prevEdge; bestSeparation = sPrev; }
+  else if (sNext > s) { increment = 1; bestEdge = nextEdge; bestSeparation = sNext; }
+  else { *edgeIndex = edge; return s; }
+  for (;;) {
+    if (increment == -1) edge = bestEdge - 1 >= 0 ? bestEdge - 1 : count1 - 1;
+    else edge = bestEdge + 1 < count1 ? bestEdge + 1 : 0;
+    s = edge_separation_230(p1, xf1, edge, p2, xf2);
+    if (s > bestSeparation) { bestEdge = edge; bestSeparation = s; }
+    else break;
+  }
+  *edgeIndex = bestEdge;
+  return bestSeparation;
+}
+
 BLCD_HDN void collide_polygons(Mf& m, const DShape& polyA, const Xf& xfA, const DShape& polyB, const Xf& xfB, bool refface_2_3_0) {
   m.count = 0;
   float totalRadius = polyA.radius + polyB.radius;
   int edgeA = 0;
-  float sepA = find_max_separation(&edgeA, polyA, xfA, polyB, xfB);
+  float sepA = refface_2_3_0 ? find_max_separation_230(&edgeA, polyA, xfA, polyB, xfB) : find_max_separation(&edgeA, polyA, xfA, polyB, xfB);
   if (sepA > totalRadius) return;
   int edgeB = 0;
-  float sepB = find_max_separation(&edgeB, polyB, xfB, polyA, xfA);
+  float sepB = refface_2_3_0 ? find_max_separation_230(&edgeB, polyB, xfB, polyA, xfA) : find_max_separation(&edgeB, polyB, xfB, polyA, xfA);
   if (sepB > totalRadius) return;
   bool useB = refface_2_3_0 ? (sepB > 0.98f * sepA + 0.001f) : (sepB > sepA + 0.1f * kLinearSlop);
   const DShape& poly1 = useB ? polyB : polyA;

@@ -300,6 +300,54 @@ inline float FindMaxSeparation(int* edgeIndex, const Shape& poly1, const Transfo
   return maxSeparation;
 }
 
+// Box2D 2.3.0's b2EdgeSeparation / hill-climbing b2FindMaxSeparation (replaced by the brute-force loop above in 2.3.1).
+// The reference's recorded Object2-cubes episode is reproduced further with the 2.3.0 rules (tests/test_gif_episodes.py),
+// so this is what pybox2d 2.3.10 appears to vendor.
+inline float EdgeSeparation230(const Shape& poly1, const Transform& xf1, int edge1, const Shape& poly2, const Transform& xf2) {
+  Vec2 normal1World = Mul(xf1.q, poly1.n[edge1]);
+  Vec2 normal1 = MulT(xf2.q, normal1World);
+  int index = 0;
+  float minDot = kMaxFloat;
+  for (int i = 0; i < poly2.count; ++i) {
+    float dot = Dot(poly2.v[i], normal1);
+    if (dot < minDot) { minDot = dot; index = i; }
+  }
+  Vec2 v1 = Mul(xf1, poly1.v[edge1]);
+  Vec2 v2 = Mul(xf2, poly2.v[index]);
+  return Dot(v2 - v1, normal1World);
+}
+
+inline float FindMaxSeparation230(int* edgeIndex, const Shape& poly1, const Transform& xf1, const Shape& poly2, const Transform& xf2) {
+  int count1 = poly1.count;
+  Vec2 d = Mul(xf2, poly2.centroid) - Mul(xf1, poly1.centroid);
+  Vec2 dLocal1 = MulT(xf1.q, d);
+  int edge = 0;
+  float maxDot = -kMaxFloat;
+  for (int i = 0; i < count1; ++i) {
+    float dot = Dot(poly1.n[i], dLocal1);
+    if (dot > maxDot) { maxDot = dot; edge = i; }
+  }
+  float s = EdgeSeparation230(poly1, xf1, edge, poly2, xf2);
+  int prevEdge = edge - 1 >= 0 ? edge - 1 : count1 - 1;
+  float sPrev = EdgeSeparation230(poly1, xf1, prevEdge, poly2, xf2);
+  int nextEdge = edge + 1 < count1 ? edge + 1 : 0;
+  float sNext = EdgeSeparation230(poly1, xf1, nextEdge, poly2, xf2);
+  int bestEdge, increment;
+  float bestSeparation;
+  if (sPrev > s && sPrev > sNext) { increment = -1; bestEdge = prevEdge; bestSeparation = sPrev; }
+  else if (sNext > s) { increment = 1; bestEdge = nextEdge; bestSeparation = sNext; }
+  else { *edgeIndex = edge; return s; }
+  for (;;) {
+    if (increment == -1) edge = bestEdge - 1 >= 0 ? bestEdge - 1 : count1 - 1;
+    else edge = bestEdge + 1 < count1 ? bestEdge + 1 : 0;
+    s = EdgeSeparation230(poly1, xf1, edge, poly2, xf2);
+    if (s > bestSeparation) { bestEdge = edge; bestSeparation = s; }
+    else break;
+  }
+  *edgeIndex = bestEdge;
+  return bestSeparation;
+}
+
 inline void FindIncidentEdge(ClipVertex c[2], const Shape& poly1, const Transform& xf1, int edge1, const Shape& poly2, const Transform& xf2) {
   Vec2 normal1 = MulT(xf2.q, Mul(xf1.q, poly1.n[edge1]));
   int index = 0;
@@ -320,10 +368,10 @@ inline void CollidePolygons(Manifold* m, const Shape& polyA, const Transform& xf
   m->pointCount = 0;
   float totalRadius = polyA.radius + polyB.radius;
   int edgeA = 0;
-  float separationA = FindMaxSeparation(&edgeA, polyA, xfA, polyB, xfB);
+  float separationA = refface_2_3_0 ? FindMaxSeparation230(&edgeA, polyA, xfA, polyB, xfB) : FindMaxSeparation(&edgeA, polyA, xfA, polyB, xfB);
   if (separationA > totalRadius) return;
   int edgeB = 0;
-  float separationB = FindMaxSeparation(&edgeB, polyB, xfB, polyA, xfA);
+  float separationB = refface_2_3_0 ? FindMaxSeparation230(&edgeB, polyB, xfB, polyA, xfA) : FindMaxSeparation(&edgeB, polyB, xfB, polyA, xfA);
   if (separationB > totalRadius) return;
   const Shape *poly1, *poly2;
   Transform xf1, xf2;

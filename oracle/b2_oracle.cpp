@@ -327,6 +327,16 @@ void* blcd_oracle_worlds_new(const blcd_spec* spec, int64_t n, uint64_t seed, in
 
 void blcd_oracle_worlds_free(void* h) { delete (Batch*)h; }
 
+// new batch holding COPIES of the listed worlds (complete simulation state: contacts, warm-start impulses, RNG, ep_t)
+void* blcd_oracle_worlds_select(void* h, const int64_t* idx, int64_t n) {
+  Batch* src = (Batch*)h;
+  Batch* b = new Batch();
+  b->spec = src->spec;
+  b->envs.reserve((size_t)n);
+  for (int64_t i = 0; i < n; ++i) b->envs.push_back(src->envs[(size_t)idx[i]]);
+  return b;
+}
+
 int blcd_oracle_worlds_reset(void* h, const int64_t* idx, int64_t n, const float* full_state, int threads) {
   Batch* b = (Batch*)h;
   if (!idx) n = (int64_t)b->envs.size();

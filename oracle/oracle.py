@@ -83,6 +83,8 @@ def _bind_worlds(l):
   l.blcd_oracle_worlds_new.argtypes = [vp, i64, C.c_uint64, i64]
   l.blcd_oracle_worlds_new.restype = vp
   l.blcd_oracle_worlds_free.argtypes = [vp]
+  l.blcd_oracle_worlds_select.argtypes = [vp, vp, i64]
+  l.blcd_oracle_worlds_select.restype = vp
   l.blcd_oracle_worlds_reset.argtypes = [vp, vp, i64, vp, i32]
   l.blcd_oracle_worlds_set_bodies.argtypes = [vp, vp, vp, i32]
   l.blcd_oracle_worlds_get_bodies.argtypes = [vp, vp]
@@ -114,6 +116,15 @@ class OracleWorlds:
       self.h = None
 
   __del__ = close
+
+  def select(self, idx):
+    """new OracleWorlds holding copies (full simulation state) of the listed worlds"""
+    idx = np.ascontiguousarray(idx, np.int64)
+    new = object.__new__(OracleWorlds)
+    new.__dict__.update(self.__dict__)
+    new.n = len(idx)
+    new.h = self.l.blcd_oracle_worlds_select(self.h, _p(idx), len(idx))
+    return new
 
   def reset(self, idx=None, full_state=None):
     idx_a = None if idx is None else np.ascontiguousarray(idx, np.int64)
