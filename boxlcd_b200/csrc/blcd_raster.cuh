@@ -80,18 +80,22 @@ BLCD_HD float edge_x_at(int ex0, int ey0, float dx, int y) { return BLCD_FADD(BL
 
 // ink of canvas row y for the filled polygon with integer vertices P (Pillow polygon_generic restated per row).
 // rules: BLCD_RASTER_PIL12 (pinned) or BLCD_RASTER_PIL9.
-BLCD_HD uint32_t polygon_row(const PolyPx& P, int y, int w, int h, int rules) {
+// ylo_in / yhi_in: the polygon's vertex row range if the caller already has it (ylo_in > yhi_in: compute here)
+BLCD_HD uint32_t polygon_row(const PolyPx& P, int y, int w, int h, int rules, int ylo_in = 1, int yhi_in = 0) {
   const int n = P.n;
   if (n <= 0) return 0u;
   // edge list: (P[i], P[i+1]) for i < n-1, plus the closing edge unless the last vertex repeats the first
   const int ne = (n > 1 && (P.x[n - 1] != P.x[0] || P.y[n - 1] != P.y[0])) ? n : n - 1;
   if (ne <= 0) return 0u;
-  int ylo = P.y[0], yhi = P.y[0];
-  for (int i = 0; i < ne; ++i) {
-    int j = i + 1 < n ? i + 1 : 0;
-    int a = P.y[i], b = P.y[j];
-    ylo = a < ylo ? a : ylo; ylo = b < ylo ? b : ylo;
-    yhi = a > yhi ? a : yhi; yhi = b > yhi ? b : yhi;
+  int ylo = ylo_in, yhi = yhi_in;
+  if (ylo_in > yhi_in) {
+    ylo = P.y[0]; yhi = P.y[0];
+    for (int i = 0; i < ne; ++i) {
+      int j = i + 1 < n ? i + 1 : 0;
+      int a = P.y[i], b = P.y[j];
+      ylo = a < ylo ? a : ylo; ylo = b < ylo ? b : ylo;
+      yhi = a > yhi ? a : yhi; yhi = b > yhi ? b : yhi;
+    }
   }
   uint32_t mask = 0u;
   const int Ymin = ylo > 0 ? ylo : 0, Ymax = yhi < h ? yhi : h;
@@ -229,7 +233,7 @@ BLCD_HD void body_px(BodyPx& o, const DShape& sh, float px, float py, float s, f
 BLCD_HD uint32_t body_px_row(const BodyPx& o, int y, int lcd_w, int lcd_h, int rules) {
   if (y < o.y0 || y > o.y1) return 0u;   // outside the shape's rows: neither the ellipse nor the polygon rules draw anything
   if (o.kind == SH_CIRCLE) return ellipse_row(o.x0, o.y0, o.x1, o.y1, y, lcd_w);
-  return polygon_row(o.P, y, lcd_w, lcd_h, rules);
+  return polygon_row(o.P, y, lcd_w, lcd_h, rules, o.y0, o.y1);
 }
 
 BLCD_HD uint32_t row_bits_from_ink(uint32_t ink, int lcd_w) {

@@ -294,12 +294,34 @@ __global__ void __launch_bounds__(kRenderThreads) k_render_poses(const DScene* s
       }
     }
   }
+  // Stage 2: work items are the (body, row) pairs that can contain ink.  They are dealt round-robin to the frame's lanes,
+  // so every lane scans a row that matters instead of most lanes rejecting most bodies; spans are OR-ed into the
+  // frame's rows in shared memory.
+  uint32_t* rowink = reinterpret_cast<uint32_t*>(bp_all + fpb * BLCD_MAX_BODIES) + f * lcd_h;
+  if (f < fpb) rowink[R] = 0u;
+  __syncthreads();
+  if (live) {
+    int total = 0;
+    for (int b = 0; b < sc.nb; ++b) {
+      int lo = max(bp[b].y0, 0), hi = min(bp[b].y1, lcd_h - 1);
+      total += max(hi - lo + 1, 0);
+    }
+    for (int item = R; item < total; item += lcd_h) {
+      int rem = item, b = 0, lo = 0;
+      for (;; ++b) {
+        lo = max(bp[b].y0, 0);
+        int cnt = max(min(bp[b].y1, lcd_h - 1) - lo + 1, 0);
+        if (rem < cnt) break;
+        rem -= cnt;
+      }
+      const int y = lo + rem;
+      uint32_t m = body_px_row(bp[b], y, lcd_w, lcd_h, sc.rules);
+      if (m) atomicOr(&rowink[y], m);
+    }
+  }
   __syncthreads();
   if (!live) return;
-  const int y = lcd_h - 1 - R;
-  uint32_t ink = 0u;
-  for (int b = 0; b < sc.nb; ++b) ink |= body_px_row(bp[b], y, lcd_w, lcd_h, sc.rules);
-  bits[w * lcd_h + R] = row_bits_from_ink(ink, lcd_w);
+  bits[w * lcd_h + R] = row_bits_from_ink(rowink[lcd_h - 1 - R], lcd_w);
 }
 
 }  // namespace
@@ -626,9 +648,9 @@ int blcd_render_poses_sized(blcd_handle h, const float* poses_dev, const uint32_
   cudaStream_t st = (cudaStream_t)stream;
   if (lcd_h > kRenderThreads) return fail("blcd_render_poses: frame height out of range");
   const int fpb = kRenderThreads / lcd_h;
-  const size_t rsm_bytes = (size_t)kSceneBytes + sizeof(BodyPx) * BLCD_MAX_BODIES * (size_t)fpb;
+  const size_t rsm_bytes = (size_t)kSceneBytes + sizeof(BodyPx) * BLCD_MAX_BODIES * (size_t)fpb + 4 * (size_t)kRenderThreads;
   if (!h->render_attr_set) {
-    CK(cudaFuncSetAttribute(k_render_poses, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kSceneBytes + sizeof(BodyPx) * BLCD_MAX_BODIES * kRenderThreads)));
+    CK(cudaFuncSetAttribute(k_render_poses, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kSceneBytes + sizeof(BodyPx) * BLCD_MAX_BODIES * kRenderThreads + 4 * kRenderThreads)));
     h->render_attr_set = true;
   }
   if (begin_timing(h, st)) return -1;

@@ -226,5 +226,8 @@ def compile_spec(world_def, G, width, height):
   sp.vel_iters, sp.pos_iters = 6 * 30, 2 * 30
   sp.ep_len = int(G.ep_len)
   sp.raster_rules = {'pil12': RASTER_PIL12, 'pil9': RASTER_PIL9}[G.get('raster_rules', 'pil12')]
+  # Box2D revision switches (FLAG_DAMPING_2_3_0 | FLAG_REFFACE_2_3_0 select the 2.3.0 forms).  Default = 2.3.1+ forms:
+  # pybox2d 2.3.10 is believed to vendor Box2D 2.3.2; the reference's recorded episodes do not discriminate (the stored
+  # Object2-cubes initial state reproduces the same 45 of 50 frames under either rule set, tests/test_gif_episodes.py).
   sp.flags = int(G.get('b2_flags', 0))
   return lay

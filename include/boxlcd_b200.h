@@ -43,10 +43,11 @@ extern "C" {
 enum { BLCD_SHAPE_CIRCLE = 0, BLCD_SHAPE_BOX = 1, BLCD_SHAPE_POLYGON = 2 };
 enum { BLCD_ROLE_OBJECT = 0, BLCD_ROLE_ROOT = 1, BLCD_ROLE_CHILD = 2 };
 enum { BLCD_RASTER_PIL12 = 0, BLCD_RASTER_PIL9 = 1 };
-/* spec.flags */
+/* spec.flags: Box2D revision switches (default 0 = the 2.3.1+ forms) and ablation switches */
 enum {
   BLCD_FLAG_DAMPING_2_3_0 = 1,   /* v *= clamp(1 - h*d, 0, 1) instead of the Pade form 1/(1+h*d) */
-  BLCD_FLAG_REFFACE_2_3_0 = 2,   /* b2CollidePolygons reference-face rule 0.98*sepA+0.001 instead of sepA+0.1*linearSlop */
+  BLCD_FLAG_REFFACE_2_3_0 = 2,   /* b2CollidePolygons as in 2.3.0: hill-climbing b2FindMaxSeparation, reference-face rule
+                                    0.98*sepA+0.001 (2.3.1+: brute-force search, sepA+0.1*linearSlop) */
   BLCD_FLAG_NO_TOI = 4,          /* continuousPhysics off (debug / ablation) */
   BLCD_FLAG_NO_SLEEP = 8         /* allowSleep off (debug / ablation) */
 };

@@ -10,12 +10,13 @@ H = np.float32(1.0 / 30.0)
 G = np.float32(-9.81)
 
 
-def worlds(env_name, n=1, G_over=None, gravity=None, flags=0):
+def worlds(env_name, n=1, G_over=None, gravity=None, flags=None):
   env = blcd.env_map[env_name](G_over or {})
   spec = env.layout.spec
   if gravity is not None:
     spec.gravity[0], spec.gravity[1] = gravity
-  spec.flags = flags
+  if flags is not None:
+    spec.flags = flags
   return env, oracle.OracleWorlds(spec, n)
 
 
