@@ -17,10 +17,10 @@ SYMBOLS = ['blcd_last_error', 'blcd_version', 'blcd_create', 'blcd_destroy', 'bl
 
 def build(force=False):
   """compile the CUDA extension in-tree for sm_100a (nvcc cross-compiles without a GPU)"""
-  srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh', '.h'))] + [os.path.join(HERE, '..', 'include', 'boxlcd_b200.h')]
+  srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh', '.h', '.cpp'))] + [os.path.join(HERE, '..', 'include', 'boxlcd_b200.h')]
   stale = force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
   if stale:
-    subprocess.run(['make', '-s', '-C', CSRC], check=True)
+    subprocess.run(['make', '-s', '-j3', '-C', CSRC], check=True)
   return LIB_PATH
 
 

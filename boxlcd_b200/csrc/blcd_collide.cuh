@@ -7,7 +7,7 @@
 #pragma once
 #include "blcd_scene.h"
 
-namespace blcd {
+namespace BLCD_NS {
 
 enum { MF_CIRCLES = 0, MF_FACE_A = 1, MF_FACE_B = 2 };
 enum { FT_VERTEX = 0, FT_FACE = 1 };
@@ -690,4 +690,4 @@ BLCD_HD Box shape_aabb(const DShape& s, const Xf& xf) {
   return bb;
 }
 
-}  // namespace blcd
+}  // namespace BLCD_NS

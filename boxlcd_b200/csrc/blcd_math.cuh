@@ -2,6 +2,7 @@
 // Operation order follows Box2D 2.3.x b2Math.h (the arithmetic behind the reference's b2World.Step,
 // boxLCD/world_env.py:446-452) so that results stay within fp32 round-off of the CPU oracle.
 #pragma once
+#include "blcd_profile.h"
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
@@ -14,7 +15,7 @@
 #define BLCD_HDN
 #endif
 
-namespace blcd {
+namespace BLCD_NS {
 
 constexpr float kPi = 3.14159265359f;
 constexpr float kEps = FLT_EPSILON;
@@ -142,4 +143,4 @@ BLCD_HD bool box_overlap(const Box& a, const Box& b) {
   return true;
 }
 
-}  // namespace blcd
+}  // namespace BLCD_NS

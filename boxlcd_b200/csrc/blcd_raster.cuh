@@ -6,13 +6,14 @@
 // ellipse, scanline polygon with apex extension) are the ones pinned against the reference in oracle/lcd_oracle.c.
 //
 // Formulation: instead of drawing shapes into an image, one call computes the ink mask of ONE canvas row for ONE shape;
-// a frame row is the OR over bodies.  A row is one uint32 (bit x = pixel x), so a frame is lcd_h coalesced 4-byte stores
+// a frame row is the OR over bodies.  A row is one RowMask (bit x = pixel x; uint32, or uint64 in the large-scene
+// profile), so a frame is lcd_h coalesced stores
 // and no atomics are needed.  The body transform is evaluated in fp32 WITHOUT fused multiply-add (Box2D's
 // b2Mul(b2Transform, b2Vec2) on x86-64), the metre->pixel scaling in fp64 with truncation toward zero, as the reference.
 #pragma once
 #include "blcd_scene.h"
 
-namespace blcd {
+namespace BLCD_NS {
 
 #ifdef __CUDA_ARCH__
 #define BLCD_FMUL(a, b) __fmul_rn(a, b)
@@ -28,13 +29,13 @@ namespace blcd {
 BLCD_HD int to_px(double v, double world_w, double lcd_w) { return (int)(v / world_w * lcd_w); }
 
 // inclusive span [x0, x1] clipped to [0, w) as a bit mask; ends are swapped if inverted (Draw.c hline)
-BLCD_HD uint32_t span_mask(int x0, int x1, int w) {
+BLCD_HD RowMask span_mask(int x0, int x1, int w) {
   if (x0 > x1) { int t = x0; x0 = x1; x1 = t; }
   if (x0 < 0) x0 = 0;
   if (x1 >= w) x1 = w - 1;
   if (x0 > x1) return 0u;
   int n = x1 - x0 + 1;
-  uint32_t m = n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u);
+  RowMask m = n >= kRowBits ? ~(RowMask)0 : (((RowMask)1 << n) - 1u);
   return m << x0;
 }
 
@@ -48,7 +49,7 @@ BLCD_HD long long ell_delta(long long a, long long b, long long x, long long y) 
 
 // ink of canvas row y for the filled ellipse inscribed in the integer box (x0, y0, x1, y1): Pillow's ellipseNew walk
 // of the first quadrant in doubled coordinates; the widest X reached at height |Y| gives the span of rows +-Y.
-BLCD_HD uint32_t ellipse_row(int x0, int y0, int x1, int y1, int y, int w) {
+BLCD_HD RowMask ellipse_row(int x0, int y0, int x1, int y1, int y, int w) {
   int a = x1 - x0, b = y1 - y0;
   if (a < 0 || b < 0 || (a == 0 && b == 0)) return 0u;
   int sy = 2 * (y - y0) - b;
@@ -81,7 +82,7 @@ BLCD_HD float edge_x_at(int ex0, int ey0, float dx, int y) { return BLCD_FADD(BL
 // ink of canvas row y for the filled polygon with integer vertices P (Pillow polygon_generic restated per row).
 // rules: BLCD_RASTER_PIL12 (pinned) or BLCD_RASTER_PIL9.
 // ylo_in / yhi_in: the polygon's vertex row range if the caller already has it (ylo_in > yhi_in: compute here)
-BLCD_HD uint32_t polygon_row(const PolyPx& P, int y, int w, int h, int rules, int ylo_in = 1, int yhi_in = 0) {
+BLCD_HD RowMask polygon_row(const PolyPx& P, int y, int w, int h, int rules, int ylo_in = 1, int yhi_in = 0) {
   const int n = P.n;
   if (n <= 0) return 0u;
   // edge list: (P[i], P[i+1]) for i < n-1, plus the closing edge unless the last vertex repeats the first
@@ -97,7 +98,7 @@ BLCD_HD uint32_t polygon_row(const PolyPx& P, int y, int w, int h, int rules, in
       yhi = a > yhi ? a : yhi; yhi = b > yhi ? b : yhi;
     }
   }
-  uint32_t mask = 0u;
+  RowMask mask = 0u;
   const int Ymin = ylo > 0 ? ylo : 0, Ymax = yhi < h ? yhi : h;
   float xx[2 * BLCD_MAX_VERTS];
   int cnt = 0;
@@ -193,7 +194,7 @@ BLCD_HD void polygon_px(PolyPx& out, const DShape& sh, float px, float py, float
 }
 
 // ink mask of canvas row y (y-up canvas coordinate) for one body
-BLCD_HD uint32_t body_row(const DShape& sh, float px, float py, float s, float c, int y, int world_w, int lcd_w, int lcd_h, int rules) {
+BLCD_HD RowMask body_row(const DShape& sh, float px, float py, float s, float c, int y, int world_w, int lcd_w, int lcd_h, int rules) {
   const double ww = (double)world_w, lw = (double)lcd_w;
   if (sh.type == SH_CIRCLE) {
     const double r = (double)sh.radius;
@@ -230,15 +231,19 @@ BLCD_HD void body_px(BodyPx& o, const DShape& sh, float px, float py, float s, f
   }
 }
 
-BLCD_HD uint32_t body_px_row(const BodyPx& o, int y, int lcd_w, int lcd_h, int rules) {
+BLCD_HD RowMask body_px_row(const BodyPx& o, int y, int lcd_w, int lcd_h, int rules) {
   if (y < o.y0 || y > o.y1) return 0u;   // outside the shape's rows: neither the ellipse nor the polygon rules draw anything
   if (o.kind == SH_CIRCLE) return ellipse_row(o.x0, o.y0, o.x1, o.y1, y, lcd_w);
   return polygon_row(o.P, y, lcd_w, lcd_h, rules, o.y0, o.y1);
 }
 
-BLCD_HD uint32_t row_bits_from_ink(uint32_t ink, int lcd_w) {
-  uint32_t full = lcd_w >= 32 ? 0xFFFFFFFFu : ((1u << lcd_w) - 1u);
+BLCD_HD RowMask row_bits_from_ink(RowMask ink, int lcd_w) {
+  RowMask full = lcd_w >= kRowBits ? ~(RowMask)0 : (((RowMask)1 << lcd_w) - 1u);
   return (~ink) & full;
 }
 
-}  // namespace blcd
+// output words per frame row (include/boxlcd_b200.h: word k = pixels 32k .. 32k+31) and word k of a row
+BLCD_HD int row_words(int lcd_w) { return BLCD_LCD_WORDS(lcd_w); }
+BLCD_HD uint32_t row_word(RowMask bits, int k) { return sizeof(RowMask) == 4 ? (uint32_t)bits : (uint32_t)((uint64_t)bits >> (32 * k)); }
+
+}  // namespace BLCD_NS

@@ -8,20 +8,21 @@
 #include "blcd_math.cuh"
 #include "boxlcd_b200.h"
 
-namespace blcd {
+namespace BLCD_NS {
 
 enum { SH_CIRCLE = 0, SH_EDGE = 1, SH_POLY = 2 };
-constexpr int kMaxPairs = 64;
-constexpr int kMaxSlots = 16;   // manifold slots per world (upper bound)
 constexpr int kSlotWords = 16;   // one persistent manifold slot
 constexpr int kBodyWords = 13;   // cx cy a vx vy w sleepTime fat(lo.x lo.y hi.x hi.y) px py (b2Body::m_xf.p)
 constexpr int kJointWords = 6;   // impulse xyz, motorImpulse, motorSpeed, limitState
-constexpr int kMiscWords = 4;    // flags, inv_dt0, ep_t, rng draws
-
-// misc flag word
-constexpr uint32_t kAwakeMask = 0xFFu;        // bit b: dynamic body b awake
-constexpr uint32_t kVariantShift = 8;         // bits 8..15: shape variant of body b
-constexpr uint32_t kNewFixtureBit = 1u << 16; // b2World::e_newFixture: run FindNewContacts at the next Step
+// misc words: flags, inv_dt0, ep_t, rng draws [, shape variants].  With at most 8 bodies the flag word holds the awake
+// bits (0..7), the shape-variant bits (8..15) and e_newFixture (16); the large profile keeps the variants in a word of
+// their own.
+constexpr bool kVariantInFlags = kMaxBodies <= 8;
+constexpr int kMiscWords = kVariantInFlags ? 4 : 5;
+constexpr uint32_t kBodyMask = (1u << kMaxBodies) - 1u;
+constexpr uint32_t kAwakeMask = kBodyMask;                                   // bit b: dynamic body b awake
+constexpr uint32_t kVariantShift = 8;                                        // (small profile) bits 8..15: shape variant of body b
+constexpr uint32_t kNewFixtureBit = kVariantInFlags ? (1u << 16) : (1u << 31); // b2World::e_newFixture: run FindNewContacts at the next Step
 
 struct DShape {
   int32_t type, count;
@@ -40,7 +41,7 @@ struct DBody {
   int32_t nvar, role, parent, root, rand_angle;
   int32_t obs[4];
   int32_t njedge;
-  int32_t jedge[BLCD_MAX_JOINTS];  // joints attached to this body, newest first (b2Body::m_jointList order)
+  int32_t jedge[kMaxJoints];  // joints attached to this body, newest first (b2Body::m_jointList order)
   double extent, joint_angle, anchor_a[2], anchor_b[2];
 };
 
@@ -59,7 +60,7 @@ struct DPair {
 struct DScene {
   int32_t nb, nj, nw, np, has_robot;
   int32_t world_w, world_h, lcd_w, lcd_h, S, P, A;
-  int32_t pobs[BLCD_MAX_OBS];
+  int32_t pobs[kMaxObs];
   int32_t nsub, vel_iters, pos_iters, ep_len, rules;
   uint32_t flags;
   float dt;
@@ -74,8 +75,8 @@ struct DScene {
   Box wallFat[BLCD_MAX_WALLS];
   V2 wall_n[BLCD_MAX_WALLS];      // unit normal of the wall's line and its offset (n . x = d), for the TOI pre-filter
   float wall_d[BLCD_MAX_WALLS];
-  DBody body[BLCD_MAX_BODIES];
-  DJoint joint[BLCD_MAX_JOINTS];
+  DBody body[kMaxBodies];
+  DJoint joint[kMaxJoints];
   DPair pair[kMaxPairs];
 };
 
@@ -208,18 +209,25 @@ inline void make_shape(DShape& s, const blcd_shape_def& sd) {
   }
 }
 
+// manifold slots per world: enough for every touching pair seen in long random rollouts of the reference scenes
+// (tests/test_hostsim_vs_oracle.py measures it); overflow is counted in BLCD_CNT_OVERFLOW, never silent
+inline int default_manifold_slots(int n_bodies) {
+  int m = n_bodies <= 2 ? 4 : (n_bodies <= 4 ? 8 : (n_bodies == 5 ? 12 : (n_bodies <= 8 ? 16 : 32)));
+  return m < kMaxSlots ? m : kMaxSlots;
+}
+
 // returns nullptr on success, else an error message
 inline const char* build_scene(DScene& sc, const blcd_spec& sp, int maxm) {
   sc = DScene();
-  if (sp.n_bodies < 1 || sp.n_bodies > BLCD_MAX_BODIES) return "n_bodies out of range";
-  if (sp.n_joints < 0 || sp.n_joints > BLCD_MAX_JOINTS) return "n_joints out of range";
+  if (sp.n_bodies < 1 || sp.n_bodies > kMaxBodies) return "n_bodies out of range for the " BLCD_PROFILE_NAME " profile";
+  if (sp.n_joints < 0 || sp.n_joints > kMaxJoints) return "n_joints out of range for the " BLCD_PROFILE_NAME " profile";
   if (sp.n_walls < 0 || sp.n_walls > BLCD_MAX_WALLS) return "n_walls out of range";
-  if (sp.lcd_w < 1 || sp.lcd_w > 32 || sp.lcd_h < 1 || sp.lcd_h > 64) return "frame size out of range (width <= 32, height <= 64)";
+  if (sp.lcd_w < 1 || sp.lcd_w > kRowBits || sp.lcd_h < 1 || sp.lcd_h > 64) return "frame size out of range for the " BLCD_PROFILE_NAME " profile";
   if (sp.obs_size != 4 * sp.n_bodies) return "obs_size must be 4 * n_bodies";
   sc.nb = sp.n_bodies; sc.nj = sp.n_joints; sc.nw = sp.n_walls; sc.has_robot = sp.has_robot;
   sc.world_w = sp.world_w; sc.world_h = sp.world_h; sc.lcd_w = sp.lcd_w; sc.lcd_h = sp.lcd_h;
   sc.S = sp.obs_size; sc.P = sp.pobs_size; sc.A = sp.act_size;
-  for (int i = 0; i < BLCD_MAX_OBS; ++i) sc.pobs[i] = sp.pobs_index[i];
+  for (int i = 0; i < kMaxObs; ++i) sc.pobs[i] = sp.pobs_index[i];   // kMaxObs <= BLCD_MAX_OBS
   sc.nsub = sp.n_substeps; sc.vel_iters = sp.vel_iters; sc.pos_iters = sp.pos_iters; sc.ep_len = sp.ep_len;
   sc.rules = sp.raster_rules; sc.flags = sp.flags; sc.dt = f32(sp.dt);
   sc.gravity = mk(f32(sp.gravity[0]), f32(sp.gravity[1]));
@@ -294,7 +302,7 @@ inline const char* build_scene(DScene& sc, const blcd_spec& sp, int maxm) {
           if ((ja == a && jb == b) || (ja == b && jb == a)) connected = true;
         }
       if (connected) continue;
-      if (sc.np >= kMaxPairs) return "scene has more than 64 collidable fixture pairs";
+      if (sc.np >= kMaxPairs) return "too many collidable fixture pairs for the " BLCD_PROFILE_NAME " profile";
       sc.pair[sc.np].fa = (uint8_t)a;
       sc.pair[sc.np].fb = (uint8_t)b;
       ++sc.np;
@@ -321,4 +329,4 @@ inline const char* build_scene(DScene& sc, const blcd_spec& sp, int maxm) {
 
 }  // namespace host
 
-}  // namespace blcd
+}  // namespace BLCD_NS

@@ -17,7 +17,7 @@
 #include "blcd_collide.cuh"
 #include "blcd_raster.cuh"
 
-namespace blcd {
+namespace BLCD_NS {
 
 constexpr int kSceneBytes = (int)((sizeof(DScene) + 15) / 16 * 16);
 
@@ -86,6 +86,7 @@ struct Philox {
 // joint record in shared memory
 enum { J_RAX = 0, J_RAY, J_RBX, J_RBY, J_EXX, J_EYX, J_EZX, J_EYY, J_EZY, J_EZZ, J_MM, J_IX, J_IY, J_IZ, J_MI, J_MS, J_PK };
 // contact record in shared memory
+// C_PK packs: body row A (bits 0..4), row B (5..9), point count (10..11), manifold slot (12..19), island (20..)
 enum { C_NX = 0, C_NY, C_FR, C_PK, C_K11, C_K12, C_K22, C_N11, C_N12, C_N22, C_PT };
 enum { P_RAX = 0, P_RAY, P_RBX, P_RBY, P_NM, P_TM, P_BIAS, P_NI, P_TI };
 // manifold slot in HBM
@@ -115,10 +116,10 @@ struct Sim {
 #define sc scene()
   Gw g;
   // body state (registers / local memory)
-  V2 c[BLCD_MAX_BODIES], c0[BLCD_MAX_BODIES], v[BLCD_MAX_BODIES];
-  float a[BLCD_MAX_BODIES], a0[BLCD_MAX_BODIES], w[BLCD_MAX_BODIES], sleepT[BLCD_MAX_BODIES], alpha0[BLCD_MAX_BODIES];
-  Xf xf[BLCD_MAX_BODIES];
-  Box fat[BLCD_MAX_BODIES];
+  V2 c[kMaxBodies], c0[kMaxBodies], v[kMaxBodies];
+  float a[kMaxBodies], a0[kMaxBodies], w[kMaxBodies], sleepT[kMaxBodies], alpha0[kMaxBodies];
+  Xf xf[kMaxBodies];
+  Box fat[kMaxBodies];
   float walpha0[BLCD_MAX_WALLS];
   uint32_t awake, variant, moved;
   bool newFixture;
@@ -135,13 +136,13 @@ struct Sim {
   // rather than in shared memory: only the records a warp actually uses occupy cache lines, so sixteen manifold slots
   // cost nothing until a world really has that many touching contacts, and shared memory is left for the body rows.
   float cr[kMaxSlots * kHotCon];
-  float jr[BLCD_MAX_JOINTS * kHotJoint];
+  float jr[kMaxJoints * kHotJoint];
   BLCD_HD uint32_t& cru(int i) { return reinterpret_cast<uint32_t*>(cr)[i]; }
   BLCD_HD uint32_t cru(int i) const { return reinterpret_cast<const uint32_t*>(cr)[i]; }
   BLCD_HD uint32_t& jru(int i) { return reinterpret_cast<uint32_t*>(jr)[i]; }
   BLCD_HD uint32_t jru(int i) const { return reinterpret_cast<const uint32_t*>(jr)[i]; }
   // islands (rebuilt every sub-step)
-  int8_t islandOf[BLCD_MAX_BODIES];
+  int8_t islandOf[kMaxBodies];
   int nIslands, nc, njo;
 
   // shared-memory row offsets and the static row index, copied out of the scene table once: the table itself sits in
@@ -235,12 +236,12 @@ struct Sim {
     const int nb = sc.nb;
     uint32_t flags = g.u(sc.off_misc + 0);
     awake = flags & kAwakeMask;
-    variant = (flags >> kVariantShift) & 0xFFu;
+    variant = kVariantInFlags ? ((flags >> kVariantShift) & kBodyMask) : g.u(sc.off_misc + 4);
     newFixture = (flags & kNewFixtureBit) != 0;
     inv_dt0 = g.f(sc.off_misc + 1);
     ep_t = (int32_t)g.u(sc.off_misc + 2);
     rng.init(seed, (uint64_t)global_world, g.u(sc.off_misc + 3));
-    for (int b = 0; b < BLCD_MAX_BODIES; ++b) {
+    for (int b = 0; b < kMaxBodies; ++b) {
       if (b < nb) {
         int o = kBodyWords * b;
         c[b] = mk(g.f(o + 0), g.f(o + 1)); a[b] = g.f(o + 2);
@@ -274,11 +275,16 @@ struct Sim {
 
   BLCD_HD void store() {
     const int nb = sc.nb;
-    g.u(sc.off_misc + 0) = (awake & kAwakeMask) | (variant << kVariantShift) | (newFixture ? kNewFixtureBit : 0u);
+    if (kVariantInFlags) {
+      g.u(sc.off_misc + 0) = (awake & kAwakeMask) | (variant << kVariantShift) | (newFixture ? kNewFixtureBit : 0u);
+    } else {
+      g.u(sc.off_misc + 0) = (awake & kAwakeMask) | (newFixture ? kNewFixtureBit : 0u);
+      g.u(sc.off_misc + 4) = variant;
+    }
     g.f(sc.off_misc + 1) = inv_dt0;
     g.u(sc.off_misc + 2) = (uint32_t)ep_t;
     g.u(sc.off_misc + 3) = rng.draws;
-    for (int b = 0; b < BLCD_MAX_BODIES; ++b) {
+    for (int b = 0; b < kMaxBodies; ++b) {
       if (b < nb) {
         int o = kBodyWords * b;
         g.f(o + 0) = c[b].x; g.f(o + 1) = c[b].y; g.f(o + 2) = a[b];
@@ -379,12 +385,12 @@ struct Sim {
   // new contact is pushed to the head of the list, as Box2D does after sorting its pair buffer.
   BLCD_HDN void find_new_contacts(uint32_t movedMask) {
     if (movedMask == 0u) return;
-    uint64_t exists = 0ull;
-    for (int k = 0; k < ncl; ++k) exists |= 1ull << clist[k];
+    PairMask exists = PairMask::none();
+    for (int k = 0; k < ncl; ++k) exists.set(clist[k]);
     for (int p = 0; p < sc.np; ++p) {
       int fa = sc.pair[p].fa, fb = sc.pair[p].fb;
       if (!(((movedMask >> fa) | (movedMask >> fb)) & 1u)) continue;
-      if ((exists >> p) & 1ull) continue;
+      if (exists.test(p)) continue;
       if (!box_overlap(ffat(fa), ffat(fb))) continue;
       for (int k = ncl; k > 0; --k) clist[k] = clist[k - 1];
       clist[0] = (uint8_t)p;
@@ -560,13 +566,13 @@ struct Sim {
         pointCount = 1;
       }
     }
-    cru(h + C_PK) = (uint32_t)rA_ | ((uint32_t)rB_ << 4) | ((uint32_t)pointCount << 8) | ((uint32_t)s << 12) | ((uint32_t)isl << 20);
+    cru(h + C_PK) = (uint32_t)rA_ | ((uint32_t)rB_ << 5) | ((uint32_t)pointCount << 10) | ((uint32_t)s << 12) | ((uint32_t)isl << 20);
   }
 
   BLCD_HD void contact_warm_start(int k) {
     const int h = kHotCon * k;
     uint32_t pk = cru(h + C_PK);
-    int rA_ = pk & 15u, rB_ = (pk >> 4) & 15u, count = (pk >> 8) & 15u;
+    int rA_ = pk & 31u, rB_ = (pk >> 5) & 31u, count = (pk >> 10) & 3u;
     float mA = hm(rA_), iA = hi(rA_), mB = hm(rB_), iB = hi(rB_);
     V2 vA = hv(rA_), vB = hv(rB_);
     float wA = hw(rA_), wB = hw(rB_);
@@ -591,7 +597,7 @@ struct Sim {
   BLCD_HD bool contact_solve_velocity(int k) {
     const int h = kHotCon * k;
     uint32_t pk = cru(h + C_PK);
-    int rA_ = pk & 15u, rB_ = (pk >> 4) & 15u, count = (pk >> 8) & 15u;
+    int rA_ = pk & 31u, rB_ = (pk >> 5) & 31u, count = (pk >> 10) & 3u;
     if (rA_ == nbS) return contact_solve_velocity_wall(h, rB_, count);
     float mA = hm(rA_), iA = hi(rA_), mB = hm(rB_), iB = hi(rB_);
     V2 vA = hv(rA_), vB = hv(rB_);
@@ -750,7 +756,7 @@ struct Sim {
   BLCD_HD void contact_store_impulses(int k) {
     const int h = kHotCon * k;
     uint32_t pk = cru(h + C_PK);
-    int count = (pk >> 8) & 15u, s = (pk >> 12) & 255u;
+    int count = (pk >> 10) & 3u, s = (pk >> 12) & 255u;
     int o = slot_base(s);
     for (int j = 0; j < 2; ++j) {
       if (j < count) {
@@ -766,7 +772,7 @@ struct Sim {
   BLCD_HD float contact_solve_position(int k, float baumgarte) {
     const int h = kHotCon * k;
     uint32_t pk = cru(h + C_PK);
-    int rA_ = pk & 15u, rB_ = (pk >> 4) & 15u, s = (pk >> 12) & 255u;
+    int rA_ = pk & 31u, rB_ = (pk >> 5) & 31u, s = (pk >> 12) & 255u;
     const int o = slot_base(s);
     uint32_t hdr = g.u(o + S_HDR);
     int p = (int)(hdr & 0xFFu), type = (int)((hdr >> 8) & 0xFFu), count = (int)((hdr >> 16) & 0xFFu);
@@ -873,7 +879,7 @@ struct Sim {
     vB += mB * P;
     wB += iB * (cross(rB, P) + motorImpulse + impz);
     jr[h + J_IX] = impx; jr[h + J_IY] = impy; jr[h + J_IZ] = impz; jr[h + J_MI] = motorImpulse;
-    jru(h + J_PK) = (uint32_t)limitState | ((uint32_t)isl << 4) | ((fixedRotation ? 1u : 0u) << 8);
+    jru(h + J_PK) = (uint32_t)limitState | ((uint32_t)isl << 4) | ((fixedRotation ? 1u : 0u) << 16);
     (void)h_dt;
     set_hv(rA_, vA, wA);
     set_hv(rB_, vB, wB);
@@ -888,7 +894,7 @@ struct Sim {
     float wA = hw(rA_), wB = hw(rB_);
     uint32_t pk = jru(h + J_PK);
     int limitState = pk & 3u;
-    bool fixedRotation = (pk >> 8) & 1u;
+    bool fixedRotation = (pk >> 16) & 1u;
     V2 rA = mk(jr[h + J_RAX], jr[h + J_RAY]), rB = mk(jr[h + J_RBX], jr[h + J_RBY]);
     if (jd.enableMotor && limitState != 3 && !fixedRotation) {
       float Cdot = wB - wA - jr[h + J_MS];
@@ -960,7 +966,7 @@ struct Sim {
     q.rowA = jd.a; q.rowB = jd.b;
     uint32_t pk = jru(h + J_PK);
     q.limitState = (int)(pk & 3u);
-    q.flags = (jd.enableMotor ? 1 : 0) | (jd.enableLimit ? 2 : 0) | (((pk >> 8) & 1u) ? 4 : 0);
+    q.flags = (jd.enableMotor ? 1 : 0) | (jd.enableLimit ? 2 : 0) | (((pk >> 16) & 1u) ? 4 : 0);
     q.rAx = jr[h + J_RAX]; q.rAy = jr[h + J_RAY]; q.rBx = jr[h + J_RBX]; q.rBy = jr[h + J_RBY];
     q.exx = jr[h + J_EXX]; q.eyx = jr[h + J_EYX]; q.ezx = jr[h + J_EZX]; q.eyy = jr[h + J_EYY]; q.ezy = jr[h + J_EZY]; q.ezz = jr[h + J_EZZ];
     q.cx = q.eyy * q.ezz - q.ezy * q.ezy; q.cy = q.ezy * q.ezx - q.eyx * q.ezz; q.cz = q.eyx * q.ezy - q.eyy * q.ezx;  // cross(ey, ez)
@@ -1043,7 +1049,7 @@ struct Sim {
     float aA = ha(rA_), aB = ha(rB_);
     uint32_t pk = jru(h + J_PK);
     int limitState = pk & 3u;
-    bool fixedRotation = (pk >> 8) & 1u;
+    bool fixedRotation = (pk >> 16) & 1u;
     float angularError = 0.0f, positionError = 0.0f;
     {
       // angular limit, branch-free: the three active cases of b2RevoluteJoint::SolvePositionConstraints differ only in
@@ -1088,13 +1094,13 @@ struct Sim {
   BLCD_HD void solve(float h_dt, float dtRatio) {
     const int nb = sc.nb;
     uint8_t corder[32];           // contact record k -> nothing to map: records are filled in solve order
-    uint8_t jorder[BLCD_MAX_JOINTS];
-    uint8_t jisl[BLCD_MAX_JOINTS];
-    uint8_t stack[BLCD_MAX_BODIES];
-    uint64_t cflag = 0ull;
+    uint8_t jorder[kMaxJoints];
+    uint8_t jisl[kMaxJoints];
+    uint8_t stack[kMaxBodies];
+    PairMask cflag = PairMask::none();
     uint32_t jflag = 0u;
     (void)corder;
-    for (int b = 0; b < BLCD_MAX_BODIES; ++b) islandOf[b] = -1;
+    for (int b = 0; b < kMaxBodies; ++b) islandOf[b] = -1;
     nIslands = 0; nc = 0; njo = 0;
     stage_rows();
     // island DFS in Box2D's order: seeds newest body first; per body its contact edges (newest first) then joint edges
@@ -1112,10 +1118,10 @@ struct Sim {
           int p = clist[k];
           int fa = sc.pair[p].fa, fb = sc.pair[p].fb;
           if (fa != fb_ && fb != fb_) continue;
-          if ((cflag >> p) & 1ull) continue;
+          if (cflag.test(p)) continue;
           int s = pslot[p];
           if (s < 0) continue;  // not touching
-          cflag |= 1ull << p;
+          cflag.set(p);
           if (nc < sc.maxm) {
             // record filled later (needs integrated velocities); remember slot + island in the packed word
             cru(kHotCon * nc + C_PK) = ((uint32_t)s << 12) | ((uint32_t)isl << 20);
@@ -1232,7 +1238,7 @@ struct Sim {
     }
     // write back + SynchronizeTransform
     if (sc.align_mode >= 4) phase_align(2); else reconverge();   // end of: position iterations
-    Xf xf1[BLCD_MAX_BODIES];
+    Xf xf1[kMaxBodies];
     for (int b = 0; b < nb; ++b) {
       if (islandOf[b] < 0) continue;
       xf1[b] = xf[b];  // transform at (c0, a0)
@@ -1286,12 +1292,12 @@ struct Sim {
     const int nb = sc.nb, nw = sc.nw;
     float toi[kMaxPairs];
     uint8_t toiCount[kMaxPairs];
-    uint64_t toiValid = 0ull, enabled = ~0ull;
+    PairMask toiValid = PairMask::none(), enabled = PairMask::all();
     for (int b = 0; b < nb; ++b) alpha0[b] = 0.0f;
     for (int i = 0; i < BLCD_MAX_WALLS; ++i) walpha0[i] = 0.0f;
     for (int k = 0; k < ncl; ++k) { toiCount[clist[k]] = 0; toi[clist[k]] = 1.0f; }
-    uint32_t toiMask[BLCD_MAX_BODIES];
-    for (int b = 0; b < BLCD_MAX_BODIES; ++b)
+    uint32_t toiMask[kMaxBodies];
+    for (int b = 0; b < kMaxBodies; ++b)
       if (b < nb) toiMask[b] = is_awake(b) ? toi_prefilter(b) : 0xFFFFFFFFu;
     for (;;) {
       // Pass 1, in contact-list order: bookkeeping of b2World::SolveTOI's scan (sweeps onto a common interval, counters)
@@ -1304,9 +1310,9 @@ struct Sim {
       int npend = 0;
       for (int k = 0; k < ncl; ++k) {
         int p = clist[k];
-        if (!((enabled >> p) & 1ull)) continue;
+        if (!enabled.test(p)) continue;
         if (toiCount[p] > kMaxSubSteps) continue;
-        if ((toiValid >> p) & 1ull) continue;
+        if (toiValid.test(p)) continue;
         int fa = sc.pair[p].fa, fb = sc.pair[p].fb;
         if (fa >= nw) continue;          // two non-bullet dynamic bodies
         int b = fb - nw;
@@ -1323,7 +1329,7 @@ struct Sim {
         ++cnt[BLCD_CNT_TOI_CALLS];
         if (!((toiMask[b] >> fa) & 1u)) {
           toi[p] = 1.0f;   // b2TimeOfImpact would come back e_separated / e_failed: alpha = 1, no side effects
-          toiValid |= 1ull << p;
+          toiValid.set(p);
         } else {
           if (npend == 16) toi_flush(pend, pend_al0, npend, toi, toiValid);
           pend_al0[npend] = walpha0[fa];
@@ -1337,9 +1343,9 @@ struct Sim {
       float minAlpha = 1.0f;
       for (int k = 0; k < ncl; ++k) {
         int p = clist[k];
-        if (!((enabled >> p) & 1ull)) continue;
+        if (!enabled.test(p)) continue;
         if (toiCount[p] > kMaxSubSteps) continue;
-        if (!((toiValid >> p) & 1ull)) continue;
+        if (!toiValid.test(p)) continue;
         float alpha = toi[p];
         if (alpha < minAlpha) { minPair = p; minAlpha = alpha; }
       }
@@ -1358,10 +1364,10 @@ struct Sim {
         walpha0[wl] = minAlpha;
       }
       bool touching = update_contact(minPair);
-      toiValid &= ~(1ull << minPair);
+      toiValid.clear(minPair);
       ++toiCount[minPair];
       if (!touching) {
-        enabled &= ~(1ull << minPair);
+        enabled.clear(minPair);
         c0[b] = bk_c0; c[b] = bk_c; a0[b] = bk_a0; a[b] = bk_a; alpha0[b] = bk_alpha0; walpha0[wl] = bk_walpha;
         xf[b] = xf_of(c[b], a[b], lc_of(b));
         continue;
@@ -1371,7 +1377,7 @@ struct Sim {
       // mini island: body b, the wall, plus the other walls b touches at this pose
       int ntc = 0;
       uint32_t wallIn = 1u << wl;
-      uint64_t inIsland = 1ull << minPair;
+      PairMask inIsland = PairMask::bit(minPair);
       cru(kHotCon * ntc + C_PK) = ((uint32_t)pslot[minPair] << 12);
       ++ntc;
       for (int k = 0; k < ncl; ++k) {
@@ -1379,19 +1385,19 @@ struct Sim {
         int fa = sc.pair[p].fa, fb = sc.pair[p].fb;
         if (fb != nw + b && fa != nw + b) continue;
         if (ntc == sc.maxm) break;
-        if ((inIsland >> p) & 1ull) continue;
+        if (inIsland.test(p)) continue;
         if (fa >= nw) continue;  // other body dynamic, no bullets: skipped
         float bkw = walpha0[fa];
         if (!((wallIn >> fa) & 1u)) walpha0[fa] = minAlpha;
         bool t2 = update_contact(p);
-        enabled |= 1ull << p;     // b2Contact::Update re-enables
+        enabled.set(p);     // b2Contact::Update re-enables
         if (!t2) { walpha0[fa] = bkw; continue; }
-        inIsland |= 1ull << p;
+        inIsland.set(p);
         cru(kHotCon * ntc + C_PK) = ((uint32_t)pslot[p] << 12);
         ++ntc;
         wallIn |= 1u << fa;
       }
-      enabled |= 1ull << minPair;
+      enabled.set(minPair);
       // b2Island::SolveTOI
       float subDt = (1.0f - minAlpha) * h_dt;
       stage_rows();
@@ -1401,7 +1407,7 @@ struct Sim {
         int p = (int)(g.u(slot_base(s) + S_HDR) & 0xFFu);
         int fA, fB;
         pair_ab(p, &fA, &fB);
-        cru(kHotCon * k + C_PK) = (uint32_t)row_of(fA) | ((uint32_t)row_of(fB) << 4) | ((uint32_t)s << 12);
+        cru(kHotCon * k + C_PK) = (uint32_t)row_of(fA) | ((uint32_t)row_of(fB) << 5) | ((uint32_t)s << 12);
       }
       for (int it = 0; it < 20; ++it) {
         float minSep = 0.0f;
@@ -1435,13 +1441,13 @@ struct Sim {
       sync_fixture(b, xf_of(c0[b], a0[b], lc_of(b)));
       for (int k = 0; k < ncl; ++k) {
         int p = clist[k];
-        if (sc.pair[p].fb == nw + b || sc.pair[p].fa == nw + b) toiValid &= ~(1ull << p);
+        if (sc.pair[p].fb == nw + b || sc.pair[p].fa == nw + b) toiValid.clear(p);
       }
       int ncl0 = ncl;
       toiMask[b] = toi_prefilter(b);   // new sweep after the event
       ph(3);   // (diagnostic build) TOI event: advance, mini-island solve
       find_new_contacts(moved);
-      for (int k = 0; k < ncl - ncl0; ++k) { toiCount[clist[k]] = 0; toi[clist[k]] = 1.0f; toiValid &= ~(1ull << clist[k]); enabled |= 1ull << clist[k]; }
+      for (int k = 0; k < ncl - ncl0; ++k) { toiCount[clist[k]] = 0; toi[clist[k]] = 1.0f; toiValid.clear(clist[k]); enabled.set(clist[k]); }
       moved = 0u;
     }
   }
@@ -1483,7 +1489,7 @@ struct Sim {
   }
 
   // run the pending time-of-impact queries (pairs wall fa x body b) against the current sweeps
-  BLCD_HD void toi_flush(const uint8_t* pend, const float* pend_al0, int& npend, float* toi, uint64_t& toiValid) {
+  BLCD_HD void toi_flush(const uint8_t* pend, const float* pend_al0, int& npend, float* toi, PairMask& toiValid) {
     for (int j = 0; j < npend; ++j) {
       int p = pend[j];
       int fa = sc.pair[p].fa, b = sc.pair[p].fb - sc.nw;
@@ -1493,7 +1499,7 @@ struct Sim {
       float t;
       int state = time_of_impact(&t, sc.wall[fa], sA, bshape(b), body_sweep(b), true);
       toi[p] = state == TOI_TOUCHING ? fminb(al0 + (1.0f - al0) * t, 1.0f) : 1.0f;
-      toiValid |= 1ull << p;
+      toiValid.set(p);
     }
     npend = 0;
   }
@@ -1561,7 +1567,7 @@ struct Sim {
     for (int k = 0; k < kMaxPairs; ++k) pslot[k] = -1;
     for (int s = 0; s < sc.maxm; ++s) g.u(slot_base(s) + S_HDR) = kSlotFree;
     for (int k = 0; k < BLCD_N_COUNTERS; ++k) cnt[k] = 0u;
-    for (int b = 0; b < BLCD_MAX_BODIES; ++b) {
+    for (int b = 0; b < kMaxBodies; ++b) {
       if (b < sc.nb) {
         Xf t;
         t.p = mk(pose[b][0], pose[b][1]);
@@ -1595,8 +1601,8 @@ struct Sim {
   }
 
   BLCD_HDN void reset(const float* full_state) {
-    float pose[BLCD_MAX_BODIES][3];
-    double angle64[BLCD_MAX_BODIES];
+    float pose[kMaxBodies][3];
+    double angle64[kMaxBodies];
     const double W = sc.world_w, H = sc.world_h;
     variant = 0u;
     for (int b = 0; b < sc.nb; ++b) {
@@ -1662,9 +1668,9 @@ struct Sim {
     out[3] = (float)sin((double)a[b]);
   }
 
-  BLCD_HD uint32_t lcd_row(int R) const {  // output row R (0 = top of the world)
+  BLCD_HD RowMask lcd_row(int R) const {  // output row R (0 = top of the world)
     int y = sc.lcd_h - 1 - R;
-    uint32_t ink = 0u;
+    RowMask ink = 0u;
     for (int b = 0; b < sc.nb; ++b)
       ink |= body_row(bshape(b), xf[b].p.x, xf[b].p.y, xf[b].q.s, xf[b].q.c, y, sc.world_w, sc.lcd_w, sc.lcd_h, sc.rules);
     return row_bits_from_ink(ink, sc.lcd_w);
@@ -1672,4 +1678,4 @@ struct Sim {
 };
 #undef sc
 
-}  // namespace blcd
+}  // namespace BLCD_NS

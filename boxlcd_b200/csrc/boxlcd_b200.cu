@@ -12,16 +12,29 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <utility>
 #include <vector>
 #include "blcd_world.cuh"
 
-using namespace blcd;
+// This file is compiled once per scene-size profile (blcd_profile.h).  Its C entry points carry the profile's prefix
+// (blcd_small_* / blcd_large_*, declared in blcd_profile_api.h); blcd_dispatch.cpp owns the public blcd_* symbols.
+#define BLCD_CAT2(a, b) a##b
+#define BLCD_CAT(a, b) BLCD_CAT2(a, b)
+#if defined(BLCD_PROFILE_LARGE)
+#define BLCD_P(name) BLCD_CAT(blcd_large_, name)
+#define BLCD_PENV blcd_large_env
+#else
+#define BLCD_P(name) BLCD_CAT(blcd_small_, name)
+#define BLCD_PENV blcd_small_env
+#endif
+#include "blcd_profile_api.h"
+
+using namespace BLCD_NS;
 
 namespace {
 
-thread_local std::string g_err;
-int fail(const std::string& msg) { g_err = msg; return -1; }
+int fail(const std::string& msg) { return blcd_fail_msg(msg.c_str()); }
 #define CK(call)                                                                                         \
   do {                                                                                                   \
     cudaError_t e_ = (call);                                                                             \
@@ -58,8 +71,8 @@ template <int BLOCK>
 __device__ __forceinline__ void write_obs(const Sim<BLOCK>& sim, const DScene& sc, const OutPtrs& o, int64_t row) {
   // row = world index (or world * T + t for rollouts)
   if (o.full_state || o.proprio) {
-    float fs[BLCD_MAX_OBS];
-    for (int b = 0; b < BLCD_MAX_BODIES; ++b) {
+    float fs[kMaxObs];
+    for (int b = 0; b < kMaxBodies; ++b) {
       if (b < sc.nb) {
         float ob[4];
         sim.obs_body(b, ob);
@@ -78,16 +91,20 @@ __device__ __forceinline__ void write_obs(const Sim<BLOCK>& sim, const DScene& s
     }
   }
   if (o.lcd_bits || o.lcd_bool) {
-    BodyPx bp[BLCD_MAX_BODIES];   // vertex transform + fp64 metre->pixel scaling once per body, not once per row
-    for (int b = 0; b < BLCD_MAX_BODIES; ++b)
+    BodyPx bp[kMaxBodies];   // vertex transform + fp64 metre->pixel scaling once per body, not once per row
+    for (int b = 0; b < kMaxBodies; ++b)
       if (b < sc.nb) body_px(bp[b], sim.bshape(b), sim.xf[b].p.x, sim.xf[b].p.y, sim.xf[b].q.s, sim.xf[b].q.c, sc.world_w, sc.lcd_w);
+    const int lw = row_words(sc.lcd_w);
     for (int R = 0; R < sc.lcd_h; ++R) {
       const int y = sc.lcd_h - 1 - R;
-      uint32_t ink = 0u;
-      for (int b = 0; b < BLCD_MAX_BODIES; ++b)
+      RowMask ink = 0u;
+      for (int b = 0; b < kMaxBodies; ++b)
         if (b < sc.nb) ink |= body_px_row(bp[b], y, sc.lcd_w, sc.lcd_h, sc.rules);
-      uint32_t bits = row_bits_from_ink(ink, sc.lcd_w);
-      if (o.lcd_bits) __stcs(o.lcd_bits + row * sc.lcd_h + R, bits);
+      RowMask bits = row_bits_from_ink(ink, sc.lcd_w);
+      if (o.lcd_bits) {
+        if (sizeof(RowMask) == 4) __stcs(o.lcd_bits + row * sc.lcd_h + R, (uint32_t)bits);
+        else for (int k = 0; k < lw; ++k) __stcs(o.lcd_bits + (row * sc.lcd_h + R) * lw + k, row_word(bits, k));
+      }
       if (o.lcd_bool)
         for (int x = 0; x < sc.lcd_w; ++x) o.lcd_bool[(row * sc.lcd_h + R) * sc.lcd_w + x] = (uint8_t)((bits >> x) & 1u);
     }
@@ -112,7 +129,7 @@ __global__ void __launch_bounds__(BLOCK) k_reset(const DScene* scene_g, uint32_t
   if (w < 0 || w >= n) return;
   Sim<BLOCK> sim(sc, hot_base<BLOCK>(smem_raw), state, n, w);
   sim.load(seed, world_offset + w);
-  float fs[BLCD_MAX_OBS];
+  float fs[kMaxObs];
   if (full_state)
     for (int k = 0; k < sc.S; ++k) fs[k] = full_state[i * sc.S + k];
   sim.reset(full_state ? fs : nullptr);
@@ -128,8 +145,8 @@ __global__ void __launch_bounds__(BLOCK) k_set_bodies(const DScene* scene_g, uin
   if (w >= n) return;
   Sim<BLOCK> sim(sc, hot_base<BLOCK>(smem_raw), state, n, w);
   sim.load(seed, world_offset + w);
-  sim.variant = variants ? (variants[w] & 0xFFu) : 0u;
-  float pose[BLCD_MAX_BODIES][3];
+  sim.variant = variants ? (variants[w] & kBodyMask) : 0u;
+  float pose[kMaxBodies][3];
   const float* src = bodies + w * sc.nb * BLCD_BODY_STATE;
   for (int b = 0; b < sc.nb; ++b) { pose[b][0] = src[b * 6]; pose[b][1] = src[b * 6 + 1]; pose[b][2] = src[b * 6 + 2]; }
   sim.build_fresh(pose);
@@ -176,7 +193,7 @@ __global__ void k_get_poses(const DScene* scene_g, const uint32_t* state, int64_
     float* dst = poses + (w * sc.nb + b) * 4;
     dst[0] = sf[(int64_t)(o + 11) * n + w]; dst[1] = sf[(int64_t)(o + 12) * n + w]; dst[2] = q.s; dst[3] = q.c;
   }
-  if (variants) variants[w] = (state[(int64_t)sc.off_misc * n + w] >> kVariantShift) & 0xFFu;
+  if (variants) variants[w] = kVariantInFlags ? ((state[(int64_t)sc.off_misc * n + w] >> kVariantShift) & kBodyMask) : state[(int64_t)(sc.off_misc + 4) * n + w];
 }
 
 template <int BLOCK>
@@ -188,7 +205,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 1 : 256 / BLOCK) k_step(
   if (w >= n) return;
   Sim<BLOCK> sim(sc, hot_base<BLOCK>(smem_raw), state, n, w);
   sim.load(seed, world_offset + w);
-  float act[BLCD_MAX_OBS];
+  float act[kMaxObs];
   for (int t = 0; t < n_steps; ++t) {
     if (actions) { for (int k = 0; k < sc.A; ++k) act[k] = actions[w * sc.A + k]; }
     else sim.draw_action(act);
@@ -211,7 +228,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 1 : 256 / BLOCK) k_rollo
   if (w >= n) return;
   Sim<BLOCK> sim(sc, hot_base<BLOCK>(smem_raw), state, n, w);
   sim.load(seed, world_offset + w);
-  float act[BLCD_MAX_OBS];
+  float act[kMaxObs];
   sim.ph_start();
   for (int t = 0; t < T; ++t) {
     int64_t row = w * T + t;
@@ -242,6 +259,9 @@ __global__ void __launch_bounds__(BLOCK) k_observe(const DScene* scene_g, uint32
 // memory -- each vertex is transformed (fp32, no FMA) and scaled to pixels (fp64, truncation) ONCE per frame by one lane
 // instead of once per row -- then every lane scans its own row over all bodies.
 constexpr int kRenderThreads = 256;
+typedef std::conditional<sizeof(RowMask) == 4, unsigned int, unsigned long long>::type RowInk;   // atomicOr operand type
+constexpr int kRenderMaxFrames = 32;   // frames per block (bounds the BodyPx staging area in shared memory)
+__host__ __device__ inline int render_frames_per_block(int lcd_h) { int f = kRenderThreads / lcd_h; return f < kRenderMaxFrames ? f : kRenderMaxFrames; }
 __global__ void __launch_bounds__(kRenderThreads) k_render_poses(const DScene* scene_g, const float* poses, const uint32_t* variants, int64_t n,
                                                                   int lcd_w, int lcd_h, uint32_t* bits) {
   extern __shared__ __align__(16) unsigned char rsm[];
@@ -254,11 +274,11 @@ __global__ void __launch_bounds__(kRenderThreads) k_render_poses(const DScene* s
     __syncthreads();
   }
   const DScene& sc = *scp;
-  const int fpb = kRenderThreads / lcd_h;                 // frames per block
+  const int fpb = render_frames_per_block(lcd_h);
   const int f = threadIdx.x / lcd_h, R = threadIdx.x - f * lcd_h;
   const int64_t w = (int64_t)blockIdx.x * fpb + f;
   const bool live = f < fpb && w < n;
-  BodyPx* bp = bp_all + f * BLCD_MAX_BODIES;
+  BodyPx* bp = bp_all + f * kMaxBodies;
   const uint32_t variant = (live && variants) ? variants[w] : 0u;
   if (live) {
     const double ww = (double)sc.world_w, lw = (double)lcd_w;
@@ -297,7 +317,7 @@ __global__ void __launch_bounds__(kRenderThreads) k_render_poses(const DScene* s
   // Stage 2: work items are the (body, row) pairs that can contain ink.  They are dealt round-robin to the frame's lanes,
   // so every lane scans a row that matters instead of most lanes rejecting most bodies; spans are OR-ed into the
   // frame's rows in shared memory.
-  uint32_t* rowink = reinterpret_cast<uint32_t*>(bp_all + fpb * BLCD_MAX_BODIES) + f * lcd_h;
+  RowInk* rowink = reinterpret_cast<RowInk*>(bp_all + fpb * kMaxBodies) + f * lcd_h;
   if (f < fpb) rowink[R] = 0u;
   __syncthreads();
   if (live) {
@@ -315,18 +335,20 @@ __global__ void __launch_bounds__(kRenderThreads) k_render_poses(const DScene* s
         rem -= cnt;
       }
       const int y = lo + rem;
-      uint32_t m = body_px_row(bp[b], y, lcd_w, lcd_h, sc.rules);
-      if (m) atomicOr(&rowink[y], m);
+      RowMask m = body_px_row(bp[b], y, lcd_w, lcd_h, sc.rules);
+      if (m) atomicOr(&rowink[y], (RowInk)m);
     }
   }
   __syncthreads();
   if (!live) return;
-  bits[w * lcd_h + R] = row_bits_from_ink(rowink[lcd_h - 1 - R], lcd_w);
+  const RowMask out = row_bits_from_ink((RowMask)rowink[lcd_h - 1 - R], lcd_w);
+  if (sizeof(RowMask) == 4) bits[w * lcd_h + R] = (uint32_t)out;
+  else for (int k = 0, lw = row_words(lcd_w); k < lw; ++k) bits[(w * lcd_h + R) * lw + k] = row_word(out, k);
 }
 
 }  // namespace
 
-struct blcd_env {
+struct BLCD_PENV {
   DScene scene;
   DScene* scene_dev = nullptr;
   uint32_t* state = nullptr;
@@ -345,10 +367,10 @@ struct blcd_env {
 
 namespace {
 
-size_t smem_bytes(const blcd_env* h, int block) { return (size_t)kSceneBytes + (size_t)h->scene.hot_words * block * sizeof(float); }
+size_t smem_bytes(const BLCD_PENV* h, int block) { return (size_t)kSceneBytes + (size_t)h->scene.hot_words * block * sizeof(float); }
 
 template <typename F>
-int launch_sized(blcd_env* h, F f) {
+int launch_sized(BLCD_PENV* h, F f) {
   switch (h->block) {
     case 64: return f(std::integral_constant<int, 64>());
     case 128: return f(std::integral_constant<int, 128>());
@@ -368,11 +390,11 @@ int set_smem_attr(K kernel, size_t bytes) {
   return 0;
 }
 
-int begin_timing(blcd_env* h, cudaStream_t st) {
+int begin_timing(BLCD_PENV* h, cudaStream_t st) {
   if (h->timing) CK(cudaEventRecord(h->ev0, st));
   return 0;
 }
-int end_timing(blcd_env* h, cudaStream_t st) {
+int end_timing(BLCD_PENV* h, cudaStream_t st) {
   if (h->timing) { CK(cudaEventRecord(h->ev1, st)); h->last_ms = -2.0f; }
   return 0;
 }
@@ -381,21 +403,16 @@ int end_timing(blcd_env* h, cudaStream_t st) {
 
 extern "C" {
 
-const char* blcd_last_error(void) { return g_err.c_str(); }
-int blcd_version(void) { return 100; }
-
-int blcd_create(const blcd_spec* spec_host, int64_t n_worlds, int device, uint64_t seed, int64_t world_offset, blcd_handle* out) {
+int BLCD_P(create)(const blcd_spec* spec_host, int64_t n_worlds, int device, uint64_t seed, int64_t world_offset, BLCD_PENV** out) {
   if (!spec_host || !out || n_worlds <= 0) return fail("blcd_create: bad arguments");
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail("blcd_create: no such CUDA device");
   CK(cudaSetDevice(device));
-  blcd_env* h = new blcd_env();
-  // manifold slots per world: enough for every touching pair seen in long random rollouts of the reference scenes
-  // (tests/test_hostsim_vs_oracle.py measures it); overflow is counted in BLCD_CNT_OVERFLOW, never silent
-  int maxm = spec_host->n_bodies <= 2 ? 4 : (spec_host->n_bodies <= 4 ? 8 : (spec_host->n_bodies == 5 ? 12 : 16));
+  BLCD_PENV* h = new BLCD_PENV();
+  int maxm = host::default_manifold_slots(spec_host->n_bodies);
   if (const char* e = getenv("BLCD_MAX_MANIFOLDS")) maxm = atoi(e);
-  if (maxm < 1 || maxm > kMaxSlots) { delete h; return fail("BLCD_MAX_MANIFOLDS must be in 1..16"); }
+  if (maxm < 1 || maxm > kMaxSlots) { delete h; return fail("BLCD_MAX_MANIFOLDS out of range for this profile"); }
   const char* err = host::build_scene(h->scene, *spec_host, maxm);
   if (err) { delete h; return fail(std::string("blcd_create: ") + err); }
   if (const char* e = getenv("BLCD_ALIGN")) h->scene.align_mode = atoi(e);
@@ -436,7 +453,7 @@ int blcd_create(const blcd_spec* spec_host, int64_t n_worlds, int device, uint64
   return 0;
 }
 
-int blcd_destroy(blcd_handle h) {
+int BLCD_P(destroy)(BLCD_PENV* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaFree(h->scene_dev);
@@ -453,7 +470,7 @@ int blcd_destroy(blcd_handle h) {
   return 0;
 }
 
-int blcd_reset(blcd_handle h, const int64_t* idx_dev, int64_t n, const float* full_state_dev, uint64_t stream) {
+int BLCD_P(reset)(BLCD_PENV* h, const int64_t* idx_dev, int64_t n, const float* full_state_dev, uint64_t stream) {
   if (!h) return fail("blcd_reset: null handle");
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
@@ -471,7 +488,7 @@ int blcd_reset(blcd_handle h, const int64_t* idx_dev, int64_t n, const float* fu
   return 0;
 }
 
-int blcd_set_bodies(blcd_handle h, const float* bodies_dev, const uint32_t* variant_dev, uint64_t stream) {
+int BLCD_P(set_bodies)(BLCD_PENV* h, const float* bodies_dev, const uint32_t* variant_dev, uint64_t stream) {
   if (!h || !bodies_dev) return fail("blcd_set_bodies: bad arguments");
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
@@ -487,7 +504,7 @@ int blcd_set_bodies(blcd_handle h, const float* bodies_dev, const uint32_t* vari
   return 0;
 }
 
-int blcd_get_bodies(blcd_handle h, float* bodies_dev, uint64_t stream) {
+int BLCD_P(get_bodies)(BLCD_PENV* h, float* bodies_dev, uint64_t stream) {
   if (!h || !bodies_dev) return fail("blcd_get_bodies: bad arguments");
   CK(cudaSetDevice(h->device));
   k_get_bodies<<<(unsigned)((h->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(h->scene_dev, h->state, h->n, bodies_dev);
@@ -496,7 +513,7 @@ int blcd_get_bodies(blcd_handle h, float* bodies_dev, uint64_t stream) {
   return 0;
 }
 
-int blcd_check_finite(blcd_handle h, uint8_t* invalid_dev, int64_t* n_invalid_host) {
+int BLCD_P(check_finite)(BLCD_PENV* h, uint8_t* invalid_dev, int64_t* n_invalid_host) {
   if (!h || !n_invalid_host) return fail("blcd_check_finite: bad arguments");
   CK(cudaSetDevice(h->device));
   unsigned long long* cnt = nullptr;
@@ -513,7 +530,7 @@ int blcd_check_finite(blcd_handle h, uint8_t* invalid_dev, int64_t* n_invalid_ho
   return 0;
 }
 
-int blcd_get_poses(blcd_handle h, float* poses_dev, uint32_t* variant_dev, uint64_t stream) {
+int BLCD_P(get_poses)(BLCD_PENV* h, float* poses_dev, uint32_t* variant_dev, uint64_t stream) {
   if (!h || !poses_dev) return fail("blcd_get_poses: bad arguments");
   CK(cudaSetDevice(h->device));
   k_get_poses<<<(unsigned)((h->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(h->scene_dev, h->state, h->n, poses_dev, variant_dev);
@@ -522,7 +539,7 @@ int blcd_get_poses(blcd_handle h, float* poses_dev, uint32_t* variant_dev, uint6
   return 0;
 }
 
-static int step_impl(blcd_handle h, const float* actions_dev, int n_steps, OutPtrs out, cudaStream_t st) {
+static int step_impl(BLCD_PENV* h, const float* actions_dev, int n_steps, OutPtrs out, cudaStream_t st) {
   if (begin_timing(h, st)) return -1;
   int rc = launch_sized(h, [&](auto B) {
     constexpr int BLOCK = decltype(B)::value;
@@ -537,14 +554,14 @@ static int step_impl(blcd_handle h, const float* actions_dev, int n_steps, OutPt
   return 0;
 }
 
-int blcd_step(blcd_handle h, const float* actions_dev, float* actions_out_dev, uint64_t stream) {
+int BLCD_P(step)(BLCD_PENV* h, const float* actions_dev, float* actions_out_dev, uint64_t stream) {
   if (!h) return fail("blcd_step: null handle");
   CK(cudaSetDevice(h->device));
   OutPtrs out = {nullptr, nullptr, nullptr, nullptr, nullptr, actions_out_dev};
   return step_impl(h, actions_dev, 1, out, (cudaStream_t)stream);
 }
 
-int blcd_step_observe(blcd_handle h, const float* actions_dev, float* actions_out_dev, float* full_state_dev, float* proprio_dev,
+int BLCD_P(step_observe)(BLCD_PENV* h, const float* actions_dev, float* actions_out_dev, float* full_state_dev, float* proprio_dev,
                       uint32_t* lcd_bits_dev, uint8_t* lcd_bool_dev, uint8_t* done_dev, uint64_t stream) {
   if (!h) return fail("blcd_step_observe: null handle");
   CK(cudaSetDevice(h->device));
@@ -552,7 +569,7 @@ int blcd_step_observe(blcd_handle h, const float* actions_dev, float* actions_ou
   return step_impl(h, actions_dev, 1, out, (cudaStream_t)stream);
 }
 
-int blcd_observe(blcd_handle h, float* full_state_dev, float* proprio_dev, uint32_t* lcd_bits_dev, uint8_t* lcd_bool_dev, uint8_t* done_dev,
+int BLCD_P(observe)(BLCD_PENV* h, float* full_state_dev, float* proprio_dev, uint32_t* lcd_bits_dev, uint8_t* lcd_bool_dev, uint8_t* done_dev,
                  uint64_t stream) {
   if (!h) return fail("blcd_observe: null handle");
   CK(cudaSetDevice(h->device));
@@ -569,7 +586,7 @@ int blcd_observe(blcd_handle h, float* full_state_dev, float* proprio_dev, uint3
   return 0;
 }
 
-int blcd_rollout(blcd_handle h, int32_t T, float* full_state_dev, uint32_t* lcd_bits_dev, float* actions_dev, uint64_t stream) {
+int BLCD_P(rollout)(BLCD_PENV* h, int32_t T, float* full_state_dev, uint32_t* lcd_bits_dev, float* actions_dev, uint64_t stream) {
   if (!h || T <= 0) return fail("blcd_rollout: bad arguments");
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
@@ -589,7 +606,7 @@ int blcd_rollout(blcd_handle h, int32_t T, float* full_state_dev, uint32_t* lcd_
 
 // pin a caller-owned host buffer once (page-locks it in place) so that later copies are direct DMA transfers; returns
 // false if the driver refuses (then the call falls back to the handle's own pinned staging buffers)
-static bool pin_user_buffer(blcd_env* h, const void* p, size_t bytes) {
+static bool pin_user_buffer(BLCD_PENV* h, const void* p, size_t bytes) {
   if (!p) return false;
   for (auto& r : h->pinned)
     if (r.first == p && r.second >= bytes) return true;
@@ -605,11 +622,11 @@ static bool pin_user_buffer(blcd_env* h, const void* p, size_t bytes) {
   return true;
 }
 
-int blcd_step_host(blcd_handle h, const float* actions_host, float* full_state_host, uint32_t* lcd_bits_host, uint8_t* done_host) {
+int BLCD_P(step_host)(BLCD_PENV* h, const float* actions_host, float* full_state_host, uint32_t* lcd_bits_host, uint8_t* done_host) {
   if (!h) return fail("blcd_step_host: null handle");
   CK(cudaSetDevice(h->device));
   const DScene& sc = h->scene;
-  size_t na = (size_t)h->n * sc.A * 4, nf = (size_t)h->n * sc.S * 4, nb = (size_t)h->n * sc.lcd_h * 4, nd = (size_t)h->n;
+  size_t na = (size_t)h->n * sc.A * 4, nf = (size_t)h->n * sc.S * 4, nb = (size_t)h->n * sc.lcd_h * row_words(sc.lcd_w) * 4, nd = (size_t)h->n;
   if (!h->d_act) {
     CK(cudaMalloc(&h->d_act, na)); CK(cudaMalloc(&h->d_fs, nf)); CK(cudaMalloc(&h->d_bits, nb)); CK(cudaMalloc(&h->d_done, nd));
     CK(cudaMallocHost(&h->h_act, na)); CK(cudaMallocHost(&h->h_fs, nf)); CK(cudaMallocHost(&h->h_bits, nb)); CK(cudaMallocHost(&h->h_done, nd));
@@ -633,24 +650,24 @@ int blcd_step_host(blcd_handle h, const float* actions_host, float* full_state_h
   return 0;
 }
 
-int blcd_render_poses(blcd_handle h, const float* poses_dev, const uint32_t* variant_dev, int64_t n, uint32_t* lcd_bits_dev, uint64_t stream) {
-  return blcd_render_poses_sized(h, poses_dev, variant_dev, n, 0, 0, lcd_bits_dev, stream);
+int BLCD_P(render_poses)(BLCD_PENV* h, const float* poses_dev, const uint32_t* variant_dev, int64_t n, uint32_t* lcd_bits_dev, uint64_t stream) {
+  return BLCD_P(render_poses_sized)(h, poses_dev, variant_dev, n, 0, 0, lcd_bits_dev, stream);
 }
 
-int blcd_render_poses_sized(blcd_handle h, const float* poses_dev, const uint32_t* variant_dev, int64_t n, int32_t lcd_w, int32_t lcd_h,
+int BLCD_P(render_poses_sized)(BLCD_PENV* h, const float* poses_dev, const uint32_t* variant_dev, int64_t n, int32_t lcd_w, int32_t lcd_h,
                             uint32_t* lcd_bits_dev, uint64_t stream) {
   if (!h || !poses_dev || !lcd_bits_dev || n < 0) return fail("blcd_render_poses: bad arguments");
   if (n == 0) return 0;
   if (lcd_w <= 0) lcd_w = h->scene.lcd_w;
   if (lcd_h <= 0) lcd_h = h->scene.lcd_h;
-  if (lcd_w > 32) return fail("blcd_render_poses: frame width > 32 needs the tiled path (not built)");
+  if (lcd_w > kRowBits) return fail("blcd_render_poses: frame too wide for the " BLCD_PROFILE_NAME " profile");
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (lcd_h > kRenderThreads) return fail("blcd_render_poses: frame height out of range");
-  const int fpb = kRenderThreads / lcd_h;
-  const size_t rsm_bytes = (size_t)kSceneBytes + sizeof(BodyPx) * BLCD_MAX_BODIES * (size_t)fpb + 4 * (size_t)kRenderThreads;
+  const int fpb = render_frames_per_block(lcd_h);
+  const size_t rsm_bytes = (size_t)kSceneBytes + sizeof(BodyPx) * kMaxBodies * (size_t)fpb + sizeof(RowInk) * (size_t)kRenderThreads;
   if (!h->render_attr_set) {
-    CK(cudaFuncSetAttribute(k_render_poses, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kSceneBytes + sizeof(BodyPx) * BLCD_MAX_BODIES * kRenderThreads + 4 * kRenderThreads)));
+    CK(cudaFuncSetAttribute(k_render_poses, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kSceneBytes + sizeof(BodyPx) * kMaxBodies * kRenderMaxFrames + sizeof(RowInk) * kRenderThreads)));
     h->render_attr_set = true;
   }
   if (begin_timing(h, st)) return -1;
@@ -661,32 +678,32 @@ int blcd_render_poses_sized(blcd_handle h, const float* poses_dev, const uint32_
   return 0;
 }
 
-int64_t blcd_state_bytes(blcd_handle h) { return h ? (int64_t)h->scene.state_words * h->n * 4 : -1; }
+int64_t BLCD_P(state_bytes)(BLCD_PENV* h) { return h ? (int64_t)h->scene.state_words * h->n * 4 : -1; }
 
-int blcd_save_state(blcd_handle h, void* buf_dev, uint64_t stream) {
+int BLCD_P(save_state)(BLCD_PENV* h, void* buf_dev, uint64_t stream) {
   if (!h || !buf_dev) return fail("blcd_save_state: bad arguments");
   CK(cudaSetDevice(h->device));
-  CK(cudaMemcpyAsync(buf_dev, h->state, (size_t)blcd_state_bytes(h), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  CK(cudaMemcpyAsync(buf_dev, h->state, (size_t)BLCD_P(state_bytes)(h), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return 0;
 }
 
-int blcd_load_state(blcd_handle h, const void* buf_dev, uint64_t stream) {
+int BLCD_P(load_state)(BLCD_PENV* h, const void* buf_dev, uint64_t stream) {
   if (!h || !buf_dev) return fail("blcd_load_state: bad arguments");
   CK(cudaSetDevice(h->device));
-  CK(cudaMemcpyAsync(h->state, buf_dev, (size_t)blcd_state_bytes(h), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  CK(cudaMemcpyAsync(h->state, buf_dev, (size_t)BLCD_P(state_bytes)(h), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return 0;
 }
 
-int64_t blcd_num_worlds(blcd_handle h) { return h ? h->n : -1; }
-int64_t blcd_kernel_launches(blcd_handle h) { return h ? h->launches : -1; }
+int64_t BLCD_P(num_worlds)(BLCD_PENV* h) { return h ? h->n : -1; }
+int64_t BLCD_P(kernel_launches)(BLCD_PENV* h) { return h ? h->launches : -1; }
 
-int blcd_enable_timing(blcd_handle h, int on) {
+int BLCD_P(enable_timing)(BLCD_PENV* h, int on) {
   if (!h) return fail("blcd_enable_timing: null handle");
   h->timing = on != 0;
   return 0;
 }
 
-int blcd_last_step_ms(blcd_handle h, float* ms_out) {
+int BLCD_P(last_step_ms)(BLCD_PENV* h, float* ms_out) {
   if (!h || !ms_out) return fail("blcd_last_step_ms: bad arguments");
   if (!h->timing || h->last_ms == -1.0f) return fail("blcd_last_step_ms: timing not enabled or nothing timed yet");
   CK(cudaSetDevice(h->device));
@@ -695,7 +712,7 @@ int blcd_last_step_ms(blcd_handle h, float* ms_out) {
   return 0;
 }
 
-int blcd_get_counters(blcd_handle h, uint32_t* counters_dev, uint64_t stream) {
+int BLCD_P(get_counters)(BLCD_PENV* h, uint32_t* counters_dev, uint64_t stream) {
   if (!h || !counters_dev) return fail("blcd_get_counters: bad arguments");
   CK(cudaSetDevice(h->device));
   // counters are BLCD_N_COUNTERS consecutive [word][world] rows: transpose with a strided 2-D copy
@@ -705,11 +722,11 @@ int blcd_get_counters(blcd_handle h, uint32_t* counters_dev, uint64_t stream) {
   return 0;
 }
 
-int blcd_scene_info(blcd_handle h, int32_t* out16) {
+int BLCD_P(scene_info)(BLCD_PENV* h, int32_t* out16) {
   if (!h || !out16) return fail("blcd_scene_info: bad arguments");
   const DScene& sc = h->scene;
   int32_t v[16] = {sc.nb, sc.nj, sc.nw, sc.np, sc.S, sc.P, sc.A, sc.lcd_w, sc.lcd_h, sc.maxm, sc.state_words, sc.hot_words, h->block,
-                   (int32_t)smem_bytes(h, h->block), 0, 0};
+                   (int32_t)smem_bytes(h, h->block), BLCD_PROFILE_ID, 0};
   memcpy(out16, v, sizeof(v));
   return 0;
 }

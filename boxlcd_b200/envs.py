@@ -1,6 +1,6 @@
 """Named environments = scene spec + per-env config defaults, the same public surface as the reference's
 `boxLCD/envs.py` (cc :5-14; Dropbox :17, Bounce :23, Bounce2 :29, Object2 :35, Object3 :41, Urchin :48, Luxo :54,
-UrchinCube :66, LuxoCube :72, UrchinBall :79, LuxoBall :86, *Balls / *Cubes :92-110)."""
+UrchinCube :66, LuxoCube :72, UrchinBall :79, LuxoBall :86, *Balls / *Cubes :92-110, Crab / CrabCube / SpiderCube :116-137)."""
 from boxlcd_b200.world_env import WorldEnv
 from boxlcd_b200.world_defs import WorldDef, Object, Robot
 from boxlcd_b200 import utils
@@ -48,4 +48,7 @@ UrchinBalls = _env('UrchinBalls', robots=['urchin'], objects=[ball_settings] * 3
 LuxoBalls = _env('LuxoBalls', robots=['luxo'], objects=[ball_settings] * 3)
 UrchinCubes = _env('UrchinCubes', robots=['urchin'], objects=[cube_settings] * 3)
 LuxoCubes = _env('LuxoCubes', robots=['luxo'], objects=[cube_settings] * 3)
-# Crab / CrabCube / SpiderCube (envs.py:116-137, lcd_base=32, up to 18 bodies) are outside the hot-path scope.
+# MORE ADVANCED: 64 x 32 frames, up to 18 bodies -- the library's large-scene profile
+Crab = _env('Crab', robots=['crab'], lcd_base=32)
+CrabCube = _env('CrabCube', robots=['crab'], objects=[dict(shape='box', size=0.4, density=1.0, friction=1.0)], lcd_base=32)
+SpiderCube = _env('SpiderCube', robots=['spider'], objects=[dict(shape='box', size=0.3, density=0.1, friction=1.0)], lcd_base=32)

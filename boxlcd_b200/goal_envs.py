@@ -61,8 +61,7 @@ class VecBodyGoalEnv(_GoalBase):
     return (self.goal['proprio'] - proprio).abs()[:, self.xy_idx].mean(1)
 
   def _ink_counts(self, bits):
-    shifts = torch.arange(self.vec.W, device=bits.device, dtype=torch.int32)
-    return (((~bits).unsqueeze(-1) >> shifts) & 1)
+    return (~self.vec.unpack_lcd(bits)).to(torch.int32)   # [N, H, W], 1 = body pixel
 
   def comp_rew_done(self, obs):
     if getattr(self.G, 'state_rew', 1):

@@ -13,7 +13,7 @@ import numpy as np
 from boxlcd_b200 import utils
 from boxlcd_b200.shapes import circleShape, polygonShape
 
-MAX_BODIES, MAX_JOINTS, MAX_WALLS, MAX_VERTS = 8, 7, 4, 8
+MAX_BODIES, MAX_JOINTS, MAX_WALLS, MAX_VERTS = 18, 17, 4, 8
 MAX_OBS = 4 * MAX_BODIES
 SHAPE_CIRCLE, SHAPE_BOX, SHAPE_POLYGON = 0, 1, 2
 ROLE_OBJECT, ROLE_ROOT, ROLE_CHILD = 0, 1, 2
@@ -216,8 +216,8 @@ def compile_spec(world_def, G, width, height):
   sp.gravity[:] = [float(world_def.gravity[0]), float(world_def.gravity[1])]
   sp.world_w, sp.world_h = int(width), int(height)
   sp.lcd_w, sp.lcd_h = int(G.lcd_base * G.wh_ratio), int(G.lcd_base)
-  if sp.lcd_w > 32:
-    raise NotImplementedError('frames wider than 32 px (lcd_base=32 crab/spider envs) are outside round-1 scope')
+  if sp.lcd_w > 64:
+    raise NotImplementedError('frames wider than 64 px')
   sp.obs_size, sp.pobs_size, sp.act_size = len(obs_keys), len(pobs_keys), len(act_keys)
   for i, k in enumerate(pobs_keys):
     sp.pobs_index[i] = obs_keys.index(k)

@@ -39,7 +39,7 @@ class VecWorldEnv:
     f32 = dict(dtype=torch.float32, device=self.device)
     self._fs = torch.empty((self.n, self.S), **f32)
     self._pr = torch.empty((self.n, self.P), **f32)
-    self._bits = torch.empty((self.n, self.H), dtype=torch.int32, device=self.device)
+    self._bits = torch.empty((self.n,) + self.bits_shape(), dtype=torch.int32, device=self.device)
     self._done = torch.empty((self.n,), dtype=torch.uint8, device=self.device)
     self._act = torch.empty((self.n, self.A), **f32)
 
@@ -58,7 +58,7 @@ class VecWorldEnv:
     out = (C.c_int32 * 16)()
     _lib.check(self.l.blcd_scene_info(self.h, out))
     keys = ['n_bodies', 'n_joints', 'n_walls', 'n_pairs', 'obs_size', 'pobs_size', 'act_size', 'lcd_w', 'lcd_h', 'manifold_slots',
-            'state_words', 'smem_words_per_world', 'block', 'smem_bytes_per_block']
+            'state_words', 'smem_words_per_world', 'block', 'smem_bytes_per_block', 'profile']
     return dict(zip(keys, list(out)))
 
   @property
@@ -91,15 +91,15 @@ class VecWorldEnv:
     """collect.py's inner loop for all worlds, T steps in one launch.  Output tensors [N, T, ...] are allocated if not given."""
     f32 = dict(dtype=torch.float32, device=self.device)
     full_state = torch.empty((self.n, T, self.S), **f32) if full_state is None else full_state
-    lcd_bits = torch.empty((self.n, T, self.H), dtype=torch.int32, device=self.device) if lcd_bits is None else lcd_bits
+    lcd_bits = torch.empty((self.n, T) + self.bits_shape(), dtype=torch.int32, device=self.device) if lcd_bits is None else lcd_bits
     actions = torch.empty((self.n, T, self.A), **f32) if actions is None else actions
     _lib.check(self.l.blcd_rollout(self.h, T, _ptr(full_state), _ptr(lcd_bits), _ptr(actions), self._stream()))
     return {'full_state': full_state, 'lcd_bits': lcd_bits, 'action': actions}
 
   def render_poses_dev(self, poses, variants=None, width=0, height=0):
-    """poses [n, B, 4] float32 (x, y, sin, cos) -> packed frames [n, H] int32"""
+    """poses [n, B, 4] float32 (x, y, sin, cos) -> packed frames [n, H] int32 ([n, H, 2] for frames wider than 32 px)"""
     n = poses.shape[0]
-    out = torch.empty((n, height or self.H), dtype=torch.int32, device=self.device)
+    out = torch.empty((n,) + self.bits_shape(height, width), dtype=torch.int32, device=self.device)
     _lib.check(self.l.blcd_render_poses_sized(self.h, _ptr(poses), _ptr(variants), n, width, height, _ptr(out), self._stream()))
     return out
 
@@ -154,11 +154,19 @@ class VecWorldEnv:
     return ms.value
 
   # -- numpy API with the reference vector-env call shape ----------------------------------------------------------------
+  def bits_shape(self, height=None, width=None):
+    """trailing shape of a packed frame: [H] words, or [H, 2] for frames wider than 32 px (include/boxlcd_b200.h)"""
+    h, w = height or self.H, width or self.W
+    return (h,) if w <= 32 else (h, (w + 31) // 32)
+
   def unpack_lcd(self, bits, width=None):
     """packed rows -> bool [..., H, W] (True = background), the reference's `lcd` observation"""
     w = width or self.W
-    shifts = torch.arange(w, device=bits.device, dtype=torch.int32)
-    return ((bits.unsqueeze(-1) >> shifts) & 1).to(torch.bool)
+    shifts = torch.arange(min(w, 32), device=bits.device, dtype=torch.int32)
+    if w <= 32:
+      return ((bits.unsqueeze(-1) >> shifts) & 1).to(torch.bool)
+    px = ((bits.unsqueeze(-1) >> shifts) & 1).to(torch.bool)     # [..., H, words, 32]
+    return px.reshape(px.shape[:-2] + (-1,))[..., :w]
 
   def _obs_numpy(self, obs):
     return {'full_state': obs['full_state'].cpu().numpy(), 'proprio': obs['proprio'].cpu().numpy(),
@@ -193,8 +201,7 @@ class VecWorldEnv:
     height = height or self.H
     if (width, height) == (self.W, self.H):
       return self.unpack_lcd(self.observe_dev()['lcd_bits']).cpu().numpy()
-    if width > 32:
-      raise NotImplementedError('frames wider than 32 px need the tiled rasterizer path (not built)')
+    # the library rejects widths its profile cannot pack (32 px small, 64 px large) with an error message
     poses, variants = self.get_poses_dev()
     bits = self.render_poses_dev(poses, variants, width, height)
     return self.unpack_lcd(bits, width).cpu().numpy()

@@ -22,6 +22,14 @@
  *     distinct threads / processes (one process per GPU is the intended multi-GPU layout).
  *   - LCD frames are bit-packed: one uint32 per output row, bit x = pixel x (1 = background,
  *     0 = body pixel, i.e. the reference's bool value), row 0 = top of the world (world_env.py:506).
+ *     Frames wider than 32 px (lcd_base=32 scenes, envs.py:116-137: 64 x 32) take BLCD_LCD_WORDS(lcd_w) = 2
+ *     words per row, word k holding pixels 32k .. 32k+31: every "[.., lcd_h] uint32" below reads
+ *     "[.., lcd_h, 2] uint32" for them.
+ *   - scenes are compiled for one of two size profiles, chosen by blcd_create from the spec: the
+ *     small profile (<= 8 bodies, <= 7 joints, <= 64 collidable fixture pairs, frames <= 32 px wide:
+ *     every env of envs.py:17-110) and the large profile (up to the BLCD_MAX_* limits, <= 128 pairs,
+ *     frames <= 64 px wide: Crab / CrabCube / SpiderCube).  Same sources, same results; the limits
+ *     only size registers, shared memory and per-world state.  BLCD_PROFILE=large forces the large one.
  *   - full_state / proprio are the reference's normalized observations (world_env.py:387-428,
  *     boxLCD/utils.py:119) as float32.
  */
@@ -34,11 +42,12 @@
 extern "C" {
 #endif
 
-#define BLCD_MAX_BODIES 8   /* dynamic bodies per world (robot root + children + objects) */
-#define BLCD_MAX_JOINTS 7
+#define BLCD_MAX_BODIES 18  /* dynamic bodies per world (robot root + children + objects); CrabCube has 18 */
+#define BLCD_MAX_JOINTS 17
 #define BLCD_MAX_WALLS 4
 #define BLCD_MAX_VERTS 8    /* b2_maxPolygonVertices */
 #define BLCD_MAX_OBS (4 * BLCD_MAX_BODIES)
+#define BLCD_LCD_WORDS(lcd_w) (((lcd_w) + 31) / 32)
 
 enum { BLCD_SHAPE_CIRCLE = 0, BLCD_SHAPE_BOX = 1, BLCD_SHAPE_POLYGON = 2 };
 enum { BLCD_ROLE_OBJECT = 0, BLCD_ROLE_ROOT = 1, BLCD_ROLE_CHILD = 2 };
@@ -153,7 +162,7 @@ int blcd_step_host(blcd_handle h, const float* actions_host, float* full_state_h
  * of every dynamic body's b2Transform; variant_dev optional [N] uint32 bitmask selecting shape variant per body. */
 int blcd_render_poses(blcd_handle h, const float* poses_dev, const uint32_t* variant_dev, int64_t n, uint32_t* lcd_bits_dev, uint64_t stream);
 
-/* Same at an explicit frame size, lcd_render(width, height) (world_env.py:460-470); 0 = the scene's own size; lcd_w <= 32. */
+/* Same at an explicit frame size, lcd_render(width, height) (world_env.py:460-470); 0 = the scene's own size; lcd_w <= 32 (small profile) or 64. */
 int blcd_render_poses_sized(blcd_handle h, const float* poses_dev, const uint32_t* variant_dev, int64_t n, int32_t lcd_w, int32_t lcd_h,
                             uint32_t* lcd_bits_dev, uint64_t stream);
 

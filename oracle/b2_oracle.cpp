@@ -402,7 +402,7 @@ int blcd_oracle_worlds_observe(void* h, float* full_state, float* proprio, uint3
   int P = sp.pobs_size > 0 ? sp.pobs_size : 1;
   parallel_for((int64_t)b->envs.size(), threads, [&](int64_t i) {
     observe_world(b->envs[(size_t)i], sp, full_state ? full_state + i * sp.obs_size : nullptr, proprio ? proprio + i * P : nullptr,
-                  lcd_bits ? lcd_bits + i * sp.lcd_h : nullptr, done ? done + i : nullptr);
+                  lcd_bits ? lcd_bits + i * sp.lcd_h * BLCD_LCD_WORDS(sp.lcd_w) : nullptr, done ? done + i : nullptr);
   });
   return 0;
 }
@@ -416,7 +416,7 @@ int blcd_oracle_worlds_rollout(void* h, int32_t T, float* full_state, uint32_t* 
     float act[BLCD_MAX_OBS];
     for (int t = 0; t < T; ++t) {
       int64_t o = i * T + t;
-      observe_world(e, sp, full_state ? full_state + o * sp.obs_size : nullptr, nullptr, lcd_bits ? lcd_bits + o * sp.lcd_h : nullptr, nullptr);
+      observe_world(e, sp, full_state ? full_state + o * sp.obs_size : nullptr, nullptr, lcd_bits ? lcd_bits + o * sp.lcd_h * BLCD_LCD_WORDS(sp.lcd_w) : nullptr, nullptr);
       draw_action(e, sp, act);
       if (actions) memcpy(actions + o * sp.act_size, act, sizeof(float) * sp.act_size);
       step_world(e, sp, act);

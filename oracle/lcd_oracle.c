@@ -186,7 +186,7 @@ static void fill_polygon(canvas* cv, const int (*P)[2], int n, int rules) {
 static int to_px(double v, int world_w, int lcd_w) { return (int)(v / (double)world_w * (double)lcd_w); }
 
 /* poses: [n, n_bodies, 4] = (px, py, sin, cos) fp32, the b2Transform of every dynamic body in draw order.
- * shapes: [n_bodies] (or [n, n_bodies] when per_world_shapes != 0).  bits: [n, lcd_h] uint32, bit x = pixel x,
+ * shapes: [n_bodies] (or [n, n_bodies] when per_world_shapes != 0).  bits: [n, lcd_h] uint32 ([n, lcd_h, 2] for 32 < lcd_w <= 64), bit x = pixel x,
  * 1 = background, row 0 = top of the world. */
 void blcd_oracle_lcd(const lcd_shape* shapes, int per_world_shapes, int n_bodies, const float* poses, int64_t n, int world_w,
                      int lcd_w, int lcd_h, int rules, uint32_t* bits) {
@@ -218,9 +218,12 @@ void blcd_oracle_lcd(const lcd_shape* shapes, int per_world_shapes, int n_bodies
     }
     for (int R = 0; R < lcd_h; ++R) {
       const uint8_t* row = &cv.ink[(lcd_h - 1 - R) * lcd_w];
-      uint32_t m = 0;
-      for (int x = 0; x < lcd_w; ++x) m |= (uint32_t)(row[x] == 0) << x;
-      bits[w * lcd_h + R] = m;
+      const int lw = (lcd_w + 31) / 32;   /* words per row: word k = pixels 32k .. 32k+31 */
+      for (int k = 0; k < lw; ++k) {
+        uint32_t m = 0;
+        for (int x = 32 * k; x < lcd_w && x < 32 * k + 32; ++x) m |= (uint32_t)(row[x] == 0) << (x - 32 * k);
+        bits[((size_t)w * lcd_h + R) * lw + k] = m;
+      }
     }
   }
 }

@@ -55,14 +55,23 @@ def lcd_render(shapes, poses, world_w, lcd_w, lcd_h, rules=0):
   shapes = np.ascontiguousarray(shapes)
   per_world = int(shapes.ndim == 2)
   assert shapes.shape[-1] == B and (not per_world or shapes.shape[0] == n)
-  bits = np.zeros((n, lcd_h), np.uint32)
+  bits = np.zeros((n,) + bits_shape(lcd_h, lcd_w), np.uint32)
   lib().blcd_oracle_lcd(shapes.ctypes.data, per_world, B, poses.ctypes.data, n, world_w, lcd_w, lcd_h, rules, bits.ctypes.data)
   return bits
 
 
+def bits_shape(lcd_h, lcd_w):
+  """trailing shape of a bit-packed frame: [H] uint32, or [H, 2] for frames wider than 32 px (include/boxlcd_b200.h)"""
+  return (lcd_h,) if lcd_w <= 32 else (lcd_h, (lcd_w + 31) // 32)
+
+
 def unpack_bits(bits, lcd_w):
-  """[..., H] uint32 -> bool [..., H, W] (the reference's lcd array; True = background)"""
-  return ((np.asarray(bits)[..., None] >> np.arange(lcd_w, dtype=np.uint32)) & 1).astype(bool)
+  """[..., H] (or [..., H, 2]) uint32 -> bool [..., H, W] (the reference's lcd array; True = background)"""
+  bits = np.asarray(bits)
+  px = ((bits[..., None] >> np.arange(32, dtype=np.uint32)) & 1).astype(bool)
+  if lcd_w > 32:
+    px = px.reshape(px.shape[:-2] + (-1,))
+  return px[..., :lcd_w]
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -157,14 +166,14 @@ class OracleWorlds:
   def observe(self):
     fs = np.zeros((self.n, self.S), np.float32)
     pr = np.zeros((self.n, self.P), np.float32)
-    bits = np.zeros((self.n, self.H), np.uint32)
+    bits = np.zeros((self.n,) + bits_shape(self.H, self.W), np.uint32)
     done = np.zeros(self.n, np.uint8)
     self.l.blcd_oracle_worlds_observe(self.h, _p(fs), _p(pr), _p(bits), _p(done), self.threads)
     return {'full_state': fs, 'proprio': pr, 'lcd_bits': bits, 'done': done.astype(bool)}
 
   def rollout(self, T, want=('full_state', 'lcd_bits', 'action')):
     fs = np.zeros((self.n, T, self.S), np.float32) if 'full_state' in want else None
-    bits = np.zeros((self.n, T, self.H), np.uint32) if 'lcd_bits' in want else None
+    bits = np.zeros((self.n, T) + bits_shape(self.H, self.W), np.uint32) if 'lcd_bits' in want else None
     act = np.zeros((self.n, T, self.A), np.float32) if 'action' in want else None
     self.l.blcd_oracle_worlds_rollout(self.h, T, _p(fs), _p(bits), _p(act), self.threads)
     return {'full_state': fs, 'lcd_bits': bits, 'action': act}

@@ -15,7 +15,7 @@ sys.path.insert(0, HERE)
 import ref_harness  # noqa: E402
 
 ENVS = ['Dropbox', 'Bounce', 'Bounce2', 'Object2', 'Object3', 'Urchin', 'Luxo', 'UrchinCube', 'LuxoCube', 'UrchinBall', 'LuxoBall',
-        'UrchinBalls', 'LuxoBalls', 'UrchinCubes', 'LuxoCubes']
+        'UrchinBalls', 'LuxoBalls', 'UrchinCubes', 'LuxoCubes', 'Crab', 'CrabCube', 'SpiderCube']
 
 
 def shape_desc(shape):

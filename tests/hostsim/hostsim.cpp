@@ -6,7 +6,7 @@
 #include <vector>
 #include "blcd_world.cuh"
 
-using namespace blcd;
+using namespace BLCD_NS;
 
 struct HostSim {
   DScene scene;
@@ -20,7 +20,7 @@ extern "C" {
 
 void* hostsim_new(const blcd_spec* spec, int64_t n, uint64_t seed, int64_t offset, int maxm) {
   HostSim* h = new HostSim();
-  if (maxm <= 0) maxm = spec->n_bodies <= 2 ? 4 : (spec->n_bodies <= 4 ? 8 : (spec->n_bodies == 5 ? 12 : 16));  // same default as blcd_create
+  if (maxm <= 0) maxm = host::default_manifold_slots(spec->n_bodies);  // same default as blcd_create
   if (host::build_scene(h->scene, *spec, maxm)) { delete h; return nullptr; }
   h->n = n; h->seed = seed; h->offset = offset;
   h->state.assign((size_t)h->scene.state_words * n, 0u);
@@ -47,8 +47,8 @@ void hostsim_set_bodies(void* p, const float* bodies, const uint32_t* variants) 
   const DScene& sc = h->scene;
   for (int64_t w = 0; w < h->n; ++w) {
     SIM(w);
-    sim.variant = variants ? (variants[w] & 0xFFu) : 0u;
-    float pose[BLCD_MAX_BODIES][3];
+    sim.variant = variants ? (variants[w] & kBodyMask) : 0u;
+    float pose[kMaxBodies][3];
     const float* src = bodies + w * sc.nb * BLCD_BODY_STATE;
     for (int b = 0; b < sc.nb; ++b) { pose[b][0] = src[b * 6]; pose[b][1] = src[b * 6 + 1]; pose[b][2] = src[b * 6 + 2]; }
     sim.build_fresh(pose);
@@ -77,12 +77,13 @@ static void write_obs(const Sim<1>& sim, const DScene& sc, float* fs_out, uint32
       for (int k = 0; k < 4; ++k) fs_out[sc.body[b].obs[k]] = ob[k];
     }
   if (bits_out) {
-    BodyPx bp[BLCD_MAX_BODIES];
+    BodyPx bp[kMaxBodies];
     for (int b = 0; b < sc.nb; ++b) body_px(bp[b], sim.bshape(b), sim.xf[b].p.x, sim.xf[b].p.y, sim.xf[b].q.s, sim.xf[b].q.c, sc.world_w, sc.lcd_w);
+    const int lw = row_words(sc.lcd_w);
     for (int R = 0; R < sc.lcd_h; ++R) {
-      uint32_t ink = 0u;
+      RowMask ink = 0u;
       for (int b = 0; b < sc.nb; ++b) ink |= body_px_row(bp[b], sc.lcd_h - 1 - R, sc.lcd_w, sc.lcd_h, sc.rules);
-      bits_out[R] = row_bits_from_ink(ink, sc.lcd_w);
+      for (int k = 0; k < lw; ++k) bits_out[R * lw + k] = row_word(row_bits_from_ink(ink, sc.lcd_w), k);
     }
   }
 }
@@ -106,7 +107,7 @@ void hostsim_observe(void* p, float* full_state, uint32_t* bits) {
   const DScene& sc = h->scene;
   for (int64_t w = 0; w < h->n; ++w) {
     SIM(w);
-    write_obs(sim, sc, full_state ? full_state + w * sc.S : nullptr, bits ? bits + w * sc.lcd_h : nullptr);
+    write_obs(sim, sc, full_state ? full_state + w * sc.S : nullptr, bits ? bits + w * sc.lcd_h * row_words(sc.lcd_w) : nullptr);
   }
 }
 
@@ -118,7 +119,7 @@ void hostsim_rollout(void* p, int T, float* full_state, uint32_t* bits, float* a
     float act[BLCD_MAX_OBS];
     for (int t = 0; t < T; ++t) {
       int64_t row = w * T + t;
-      write_obs(sim, sc, full_state ? full_state + row * sc.S : nullptr, bits ? bits + row * sc.lcd_h : nullptr);
+      write_obs(sim, sc, full_state ? full_state + row * sc.S : nullptr, bits ? bits + row * sc.lcd_h * row_words(sc.lcd_w) : nullptr);
       sim.draw_action(act);
       if (actions) memcpy(actions + row * sc.A, act, sizeof(float) * sc.A);
       sim.env_step(act);
@@ -140,12 +141,13 @@ void hostsim_render_poses(void* p, const float* poses, const uint32_t* variants,
   if (lcd_h <= 0) lcd_h = sc.lcd_h;
   for (int64_t w = 0; w < n; ++w)
     for (int R = 0; R < lcd_h; ++R) {
-      uint32_t ink = 0u, variant = variants ? variants[w] : 0u;
+      RowMask ink = 0u;
+      uint32_t variant = variants ? variants[w] : 0u;
       for (int b = 0; b < sc.nb; ++b) {
         const float* q = poses + (w * sc.nb + b) * 4;
         ink |= body_row(sc.body[b].shape[(variant >> b) & 1u], q[0], q[1], q[2], q[3], lcd_h - 1 - R, sc.world_w, lcd_w, lcd_h, sc.rules);
       }
-      bits[w * lcd_h + R] = row_bits_from_ink(ink, lcd_w);
+      for (int k = 0, lw = row_words(lcd_w); k < lw; ++k) bits[(w * lcd_h + R) * lw + k] = row_word(row_bits_from_ink(ink, lcd_w), k);
     }
 }
 

@@ -5,16 +5,22 @@ import subprocess
 import numpy as np
 
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'hostsim')
-LIB = os.path.join(HERE, '_build', 'libhostsim.so')
-_lib = None
+LIB = os.path.join(HERE, '_build', 'libhostsim.so')               # small profile (boxlcd_b200/csrc/blcd_profile.h)
+LIB_LARGE = os.path.join(HERE, '_build', 'libhostsim_large.so')   # large profile
+_libs = {}
 
 
-def lib():
-  global _lib
-  if _lib is None:
-    if LIB.endswith('libhostsim.so'):
+def fits_small(spec):
+  """same rule as blcd_create (boxlcd_b200/csrc/blcd_dispatch.cpp)"""
+  return spec.n_bodies <= 8 and spec.n_joints <= 7 and spec.lcd_w <= 32
+
+
+def lib(large=False):
+  path = LIB_LARGE if large else LIB
+  if path not in _libs:
+    if path.endswith(('libhostsim.so', 'libhostsim_large.so')):
       subprocess.run(['make', '-s', '-C', HERE], check=True)
-    l = C.CDLL(LIB)
+    l = C.CDLL(path)
     vp, i64 = C.c_void_p, C.c_int64
     l.hostsim_new.argtypes = [vp, i64, C.c_uint64, i64, C.c_int]
     l.hostsim_new.restype = vp
@@ -27,8 +33,8 @@ def lib():
     l.hostsim_rollout.argtypes = [vp, C.c_int, vp, vp, vp]
     l.hostsim_counters.argtypes = [vp, vp]
     l.hostsim_render_poses.argtypes = [vp, vp, vp, i64, C.c_int, C.c_int, vp]
-    _lib = l
-  return _lib
+    _libs[path] = l
+  return _libs[path]
 
 
 def _p(a):
@@ -36,12 +42,16 @@ def _p(a):
 
 
 class HostSim:
-  def __init__(self, spec, n, seed=0, world_offset=0, maxm=0):
-    self.l = lib()
+  def __init__(self, spec, n, seed=0, world_offset=0, maxm=0, profile=None):
+    self.l = lib(large=(profile == 'large') or (profile is None and not fits_small(spec)))
     self.spec, self.n = spec, int(n)
     self.h = self.l.hostsim_new(C.byref(spec), self.n, seed, world_offset, maxm)
     assert self.h, 'scene rejected'
     self.B, self.S, self.A, self.H, self.W = spec.n_bodies, spec.obs_size, spec.act_size, spec.lcd_h, spec.lcd_w
+
+  def _rows(self, h=None, w=None):
+    h, w = h or self.H, w or self.W
+    return (h,) if w <= 32 else (h, (w + 31) // 32)
 
   def __del__(self):
     if getattr(self, 'h', None):
@@ -70,13 +80,13 @@ class HostSim:
 
   def observe(self):
     fs = np.zeros((self.n, self.S), np.float32)
-    bits = np.zeros((self.n, self.H), np.uint32)
+    bits = np.zeros((self.n,) + self._rows(), np.uint32)
     self.l.hostsim_observe(self.h, _p(fs), _p(bits))
     return {'full_state': fs, 'lcd_bits': bits}
 
   def rollout(self, T):
     fs = np.zeros((self.n, T, self.S), np.float32)
-    bits = np.zeros((self.n, T, self.H), np.uint32)
+    bits = np.zeros((self.n, T) + self._rows(), np.uint32)
     act = np.zeros((self.n, T, self.A), np.float32)
     self.l.hostsim_rollout(self.h, T, _p(fs), _p(bits), _p(act))
     return {'full_state': fs, 'lcd_bits': bits, 'action': act}
@@ -90,6 +100,6 @@ class HostSim:
     poses = np.ascontiguousarray(poses, np.float32)
     n = poses.shape[0]
     v = None if variants is None else np.ascontiguousarray(variants, np.uint32)
-    bits = np.zeros((n, lcd_h or self.H), np.uint32)
+    bits = np.zeros((n,) + self._rows(lcd_h or self.H, lcd_w or self.W), np.uint32)
     self.l.hostsim_render_poses(self.h, _p(poses), _p(v), n, lcd_w, lcd_h, _p(bits))
     return bits

@@ -7,6 +7,7 @@ ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import hostsim_py
 hostsim_py.LIB = os.path.join(ROOT, 'tests', 'hostsim', '_build', 'libhostsim_asan.so')
+hostsim_py.LIB_LARGE = os.path.join(ROOT, 'tests', 'hostsim', '_build', 'libhostsim_large_asan.so')
 import boxlcd_b200 as b
 from hostsim_py import HostSim
 for name in sorted(b.env_map):
