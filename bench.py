@@ -22,7 +22,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ALG_BYTES = lambda sp: 4 * sp.lcd_h + 4 * sp.obs_size + 4 * sp.act_size   # packed frame + full_state + action, SURVEY 8(d)
+ALG_BYTES = lambda sp: 4 * sp.lcd_h * ((sp.lcd_w + 31) // 32) + 4 * sp.obs_size + 4 * sp.act_size   # packed frame + full_state + action, SURVEY 8(d)
 
 
 def parse():
@@ -172,7 +172,7 @@ def main():
   out = v.rollout_dev(1)  # allocate nothing big yet; touch the path once
   f32 = dict(dtype=torch.float32, device=dev)
   fs = torch.empty((n, T, v.S), **f32)
-  bits = torch.empty((n, T, v.H), dtype=torch.int32, device=dev)
+  bits = torch.empty((n, T) + v.bits_shape(), dtype=torch.int32, device=dev)
   act = torch.empty((n, T, v.A), **f32)
 
   def one_step():
@@ -229,7 +229,7 @@ def main():
     from boxlcd_b200 import _lib
     h_act = np.random.RandomState(rank).uniform(-1, 1, (ne, ve.A)).astype(np.float32)
     h_fs = np.zeros((ne, ve.S), np.float32)
-    h_bits = np.zeros((ne, ve.H), np.uint32)
+    h_bits = np.zeros((ne,) + ve.bits_shape(), np.uint32)
     h_done = np.zeros(ne, np.uint8)
     Te = min(T, 20)
     def e2e_pass(k):
@@ -255,7 +255,6 @@ def main():
     nr = 4 * 1024 * 1024
     poses, _ = v.get_poses_dev()
     poses = poses[torch.randint(0, n, (nr,), device=dev)].contiguous()
-    out_bits = torch.empty((nr, v.H), dtype=torch.int32, device=dev)
     for _ in range(3):
       v.render_poses_dev(poses)
     torch.cuda.synchronize()
@@ -266,10 +265,11 @@ def main():
     r1.record()
     torch.cuda.synchronize()
     r_ms = r0.elapsed_time(r1) / 5
-    r_bytes = nr * (16 * v.B + 4 * v.H)
-    render = {'kernel': 'k_render_poses', 'frames': nr, 'ms': r_ms, 'frames_per_s': nr / (r_ms / 1e3), 'algorithmic_bytes_per_frame': 16 * v.B + 4 * v.H,
+    frame_words = int(np.prod(v.bits_shape()))
+    r_bytes = nr * (16 * v.B + 4 * frame_words)
+    render = {'kernel': 'k_render_poses', 'frames': nr, 'ms': r_ms, 'frames_per_s': nr / (r_ms / 1e3), 'algorithmic_bytes_per_frame': 16 * v.B + 4 * frame_words,
               'achieved_gbs': r_bytes / (r_ms / 1e3) / 1e9}
-    del poses, out_bits
+    del poses
   if rank != 0:
     if world_size > 1:
       dist.destroy_process_group()

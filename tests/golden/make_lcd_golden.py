@@ -6,7 +6,7 @@ The fixture pins oracle/lcd_oracle.c (tests/test_lcd_oracle.py) and, through it,
 
 Per env the file holds: poses [n,B,4] f32 (x, y, sin, cos of each dynamic body's b2Transform, draw order), per-world
 shape tables (kind [n,B], nvert [n,B], radius [n,B], verts [n,B,8,2]) and the reference frame bit-packed as
-bits [n,H] uint32 (bit x = pixel x, 1 = background), plus meta = (WIDTH, W, H).
+bits [n,H] uint32 (bit x = pixel x, 1 = background; [n,H,2] for the 64-px-wide Crab / SpiderCube frames), plus meta = (WIDTH, W, H).
 """
 import os
 import sys
@@ -17,12 +17,17 @@ sys.path.insert(0, HERE)
 import ref_harness  # noqa: E402
 
 F = np.float32
-ENVS = ['Dropbox', 'Bounce2', 'Object2', 'Urchin', 'Luxo', 'UrchinCube', 'LuxoCube', 'UrchinBall', 'LuxoBall']
+ENVS = ['Dropbox', 'Bounce2', 'Object2', 'Urchin', 'Luxo', 'UrchinCube', 'LuxoCube', 'UrchinBall', 'LuxoBall', 'Crab', 'SpiderCube']
 
 
 def pack_bits(lcd):
+  """[H, W] bool -> [H] uint32, or [H, 2] (word k = pixels 32k .. 32k+31) for frames wider than 32 px"""
   H, W = lcd.shape
-  return (lcd.astype(np.uint64) << np.arange(W, dtype=np.uint64)[None]).sum(1).astype(np.uint32)
+  if W <= 32:
+    return (lcd.astype(np.uint64) << np.arange(W, dtype=np.uint64)[None]).sum(1).astype(np.uint32)
+  pad = np.zeros((H, 64), np.uint64)
+  pad[:, :W] = lcd
+  return (pad.reshape(H, 2, 32) << np.arange(32, dtype=np.uint64)).sum(2).astype(np.uint32)
 
 
 def shape_row(body):

@@ -24,7 +24,7 @@ def i32(a):
   return np.ascontiguousarray(a).view(np.int32)
 
 
-@pytest.mark.parametrize('name', ['Dropbox', 'Bounce2', 'Object2', 'Urchin', 'Luxo', 'UrchinCube', 'LuxoCube', 'UrchinBall', 'LuxoBall'])
+@pytest.mark.parametrize('name', ['Dropbox', 'Bounce2', 'Object2', 'Urchin', 'Luxo', 'UrchinCube', 'LuxoCube', 'UrchinBall', 'LuxoBall', 'Crab', 'SpiderCube'])
 def test_frames_bit_exact_vs_reference_golden(name):
   gold = np.load(GOLD)
   env = make_env(name)

@@ -27,7 +27,7 @@ def test_rollouts_bit_exact(name):
   assert (co == ch).all()
 
 
-@pytest.mark.parametrize('name', ['Urchin', 'LuxoCube', 'UrchinBall', 'Object2', 'Bounce2'])
+@pytest.mark.parametrize('name', ['Urchin', 'LuxoCube', 'UrchinBall', 'Object2', 'Bounce2', 'CrabCube', 'SpiderCube'])
 def test_single_steps_from_fresh_states_bit_exact(name):
   env = make_env(name)
   rng = np.random.RandomState(5)
@@ -59,7 +59,7 @@ def test_reset_from_full_state_bit_exact():
 def test_host_rasterizer_matches_reference_golden_frames():
   import os
   gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'lcd_golden.npz'))
-  for name in ['Dropbox', 'Bounce2', 'Object2', 'Urchin', 'Luxo', 'UrchinCube', 'LuxoCube', 'UrchinBall', 'LuxoBall']:
+  for name in ['Dropbox', 'Bounce2', 'Object2', 'Urchin', 'Luxo', 'UrchinCube', 'LuxoCube', 'UrchinBall', 'LuxoBall', 'Crab', 'SpiderCube']:
     env = make_env(name)
     hs = HostSim(env.layout.spec, 1)
     kind = gold[f'{name}_kind']
@@ -67,4 +67,17 @@ def test_host_rasterizer_matches_reference_golden_frames():
     if not any(env.layout.spec.bodies[b].n_variants > 1 for b in range(kind.shape[1])):
       variants = None
     bits = hs.render_poses(gold[f'{name}_poses'], variants)
-    assert (bits == gold[f'{name}_bits']).all(), name
+    assert bits.shape == gold[f'{name}_bits'].shape and (bits == gold[f'{name}_bits']).all(), name
+
+
+@pytest.mark.parametrize('name', ['Urchin', 'LuxoCubes', 'Object3', 'UrchinBall'])
+def test_large_profile_build_is_bit_identical_on_small_scenes(name):
+  """the two scene-size profiles (csrc/blcd_profile.h) are the same source with different limits: same results"""
+  env = make_env(name)
+  n, T = 16, 40
+  a, b = HostSim(env.layout.spec, n, seed=4, profile='small'), HostSim(env.layout.spec, n, seed=4, profile='large')
+  a.reset(); b.reset()
+  ra, rb = a.rollout(T), b.rollout(T)
+  for k in ra:
+    assert (ra[k] == rb[k]).all(), k
+  assert (a.counters() == b.counters()).all()

@@ -8,7 +8,7 @@ import pytest
 from oracle import oracle
 
 GOLD = os.path.join(os.path.dirname(__file__), 'golden', 'lcd_golden.npz')
-ENVS = ['Dropbox', 'Bounce2', 'Object2', 'Urchin', 'Luxo', 'UrchinCube', 'LuxoCube', 'UrchinBall', 'LuxoBall']
+ENVS = ['Dropbox', 'Bounce2', 'Object2', 'Urchin', 'Luxo', 'UrchinCube', 'LuxoCube', 'UrchinBall', 'LuxoBall', 'Crab', 'SpiderCube']
 
 
 @pytest.fixture(scope='module')
@@ -21,13 +21,14 @@ def test_oracle_matches_reference_golden_frames(gold, env):
   shapes = oracle.make_shapes(gold[f'{env}_kind'], gold[f'{env}_nvert'], gold[f'{env}_radius'], gold[f'{env}_verts'])
   world_w, lcd_w, lcd_h = [int(x) for x in gold[f'{env}_meta']]
   bits = oracle.lcd_render(shapes, gold[f'{env}_poses'], world_w, lcd_w, lcd_h)
-  bad = np.nonzero((bits != gold[f'{env}_bits']).any(1))[0]
+  assert bits.shape == gold[f'{env}_bits'].shape
+  bad = np.nonzero((bits != gold[f'{env}_bits']).reshape(len(bits), -1).any(1))[0]
   assert len(bad) == 0, f'{env}: {len(bad)} / {len(bits)} frames differ, first {bad[:5]}'
-  assert (bits != (1 << lcd_w) - 1 if lcd_w < 32 else bits != 0xFFFFFFFF).any(), 'frames are empty'
+  assert (~oracle.unpack_bits(bits, lcd_w)).any(), 'frames are empty'
 
 
 @pytest.mark.reference
-@pytest.mark.parametrize('env', ['Urchin', 'LuxoCube', 'UrchinBall', 'Object2'])
+@pytest.mark.parametrize('env', ['Urchin', 'LuxoCube', 'UrchinBall', 'Object2', 'CrabCube'])
 def test_oracle_matches_live_reference(env):
   sys.path.insert(0, os.path.join(os.path.dirname(__file__), 'golden'))
   import ref_harness
