@@ -5,7 +5,7 @@ Follows the reference's construction order so indices mean the same thing on bot
   * dynamic bodies in `dynbodies` insertion order (world_env.py:197-304): per robot root, then children in
     `robot.joints` order, then objects -- this is also the LCD draw order (world_env.py:478);
   * joints in creation order (world_env.py:255-267);
-  * walls in creation order (world_env.py:311-314);
+  * walls in creation order (world_env.py:311-314), or the single floor edge of walls=0 (:316);
   * observation keys sorted alphabetically (world_env.py:119-126), action keys likewise (:138-141).
 """
 import ctypes as C
@@ -110,8 +110,8 @@ def compile_spec(world_def, G, width, height):
                               'all_corners is unusable in the reference too (ipdb.set_trace at world_env.py:178)')
   if not G.use_speed:
     raise NotImplementedError('torque control is broken in the reference (act key :force vs lookup :torque, world_env.py:114,443) and is not built')
-  if not G.walls:
-    raise NotImplementedError('walls=0 (scrolling floor) is outside round-1 scope (SURVEY.md section 8f-4)')
+  if not G.walls and not world_def.robots:
+    raise IndexError('walls=0 needs a robot to follow (world_env.py:382 indexes world_def.robots[0])')
   lay = SceneLayout()
   sp = lay.spec
   A = utils.A
@@ -209,7 +209,10 @@ def compile_spec(world_def, G, width, height):
     lay.body_names.append(obj.name)
     nb += 1
   sp.n_bodies, sp.n_joints, sp.has_robot = nb, nj, int(len(world_def.robots) > 0)
-  walls = [(0, 0, width, 0), (0, 0, 0, height), (width, 0, width, height), (0, height, width, height)]
+  if G.walls:
+    walls = [(0, 0, width, 0), (0, 0, 0, height), (width, 0, width, height), (0, height, width, height)]
+  else:   # open world: one long floor edge, nothing else (world_env.py:316); frames keep showing [0, WIDTH) (:462 "TODO")
+    walls = [(-1000 * width, 0, 1000 * width, 0)]
   sp.n_walls = len(walls)
   for i, w in enumerate(walls):
     sp.walls[i][:] = [float(x) for x in w]

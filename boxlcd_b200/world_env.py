@@ -110,14 +110,22 @@ class WorldEnv:
       full_state[self.pobs_idxs] = proprio
     vec = self._sim()
     obs = vec.reset(full_state=None if full_state is None else np.asarray(full_state, np.float32)[None])
-    return self._unbatch(obs)
+    return self._unbatch(self._follow(obs))
 
   def step(self, action):
     """world_env.py:431-458"""
     self.ep_t += 1
     obs, rew, done, infos = self._sim().step(np.asarray(action, np.float32).reshape(1, self.act_size))
     done = bool(done[0])
-    return self._unbatch(obs), 0.0, done, {'timeout': done}
+    return self._unbatch(self._follow(obs)), 0.0, done, {'timeout': done}
+
+  def _follow(self, obs):
+    """walls=0: the view offset tracks the first robot's root (world_env.py:381-382, 453-454; frames ignore it, :462)"""
+    if not self.G.walls:
+      robot = self.world_def.robots[0]
+      x01 = float(obs['full_state'][0, self.obs_keys.index(f'{robot.type}0:root:x:p')])   # normalized to [-1, 1] over [0, WIDTH]
+      self.scroll = (x01 + 1.0) * 0.5 * self.WIDTH - self.VIEWPORT_W / SCALE / 2
+    return obs
 
   def _get_obs(self):
     return self._unbatch(self._sim().observe())

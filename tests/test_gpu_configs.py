@@ -160,8 +160,8 @@ def test_errors_are_loud():
   with pytest.raises(RuntimeError, match='too wide'):
     poses, var = v.get_poses_dev()
     v.render_poses_dev(poses, None, 40, 16)
-  with pytest.raises(NotImplementedError):
-    blcd.envs.Urchin({'walls': 0})
+  with pytest.raises(IndexError):
+    blcd.envs.Dropbox({'walls': 0})     # the reference indexes robots[0] for the scroll offset (world_env.py:382)
   with pytest.raises(NotImplementedError):
     blcd.envs.Urchin().lcd_render(lcd_mode='RGB')
 
@@ -195,3 +195,25 @@ def test_failure_detection_flags_and_resets_non_finite_worlds():
   assert n_bad == 2 and flags.cpu().numpy().nonzero()[0].tolist() == [5, 9]
   v.check_finite(auto_reset=True)
   assert v.check_finite()[0] == 0 and np.isfinite(v.get_bodies()).all()
+
+
+def test_open_world_without_walls_matches_oracle_and_tracks_scroll():
+  """walls=0 (world_env.py:316, 381-382, 453-454)"""
+  env = make_env('Urchin', walls=0)
+  n = 2048
+  ow = oracle.OracleWorlds(env.layout.spec, n, seed=6, threads=8)
+  ow.reset()
+  v = vec(env, n, seed=6)
+  v.reset_dev()
+  assert np.abs(v.get_bodies() - ow.get_bodies()).max() < 2e-6
+  act = np.random.RandomState(1).uniform(-1, 1, (n, 3)).astype(np.float32)
+  ow.step(act)
+  v.step_dev(torch.as_tensor(act).cuda(), observe=False)
+  assert (np.abs(v.get_bodies()[..., :3] - ow.get_bodies()[..., :3]).max((1, 2)) < 1e-5).mean() > 0.98
+  r = v.rollout_dev(100)
+  fs = r['full_state'].cpu().numpy()
+  assert np.isfinite(fs).all() and (np.abs(fs[:, -1, env.obs_keys.index('urchin0:root:x:p')]) > 1.0).any()   # left the frame
+  e1 = make_env('Urchin', walls=0)
+  obs = e1.reset()
+  x = (obs['full_state'][e1.obs_keys.index('urchin0:root:x:p')] + 1) / 2 * e1.WIDTH
+  assert abs(e1.scroll - (x - e1.WIDTH / 2)) < 1e-6

@@ -81,3 +81,20 @@ def test_large_profile_build_is_bit_identical_on_small_scenes(name):
   for k in ra:
     assert (ra[k] == rb[k]).all(), k
   assert (a.counters() == b.counters()).all()
+
+
+@pytest.mark.parametrize('name', ['Urchin', 'LuxoCube', 'SpiderCube'])
+def test_open_world_floor_only_bit_exact(name):
+  """walls=0 (world_env.py:316): one long floor edge, bodies may leave the frame"""
+  env = make_env(name, walls=0)
+  sp = env.layout.spec
+  assert sp.n_walls == 1 and tuple(sp.walls[0]) == (-1000.0 * env.WIDTH, 0.0, 1000.0 * env.WIDTH, 0.0)
+  n, T = 24, 60
+  ow, hs = oracle.OracleWorlds(sp, n, seed=2, threads=4), HostSim(sp, n, seed=2)
+  ow.reset(); hs.reset()
+  ro, rh = ow.rollout(T), hs.rollout(T)
+  for k in ro:
+    assert (ro[k] == rh[k]).all(), k
+  b = ow.get_bodies()
+  assert np.isfinite(b).all() and b[..., 1].min() > 0.0          # nothing falls through the floor
+  assert (b[..., 0] < 0).any() or (b[..., 0] > env.WIDTH).any()    # and nothing keeps the robots inside [0, WIDTH]
