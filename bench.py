@@ -227,16 +227,18 @@ def main():
     ve = v if ne == n else VecWorldEnv(env, ne, device=dev, seed=0, world_offset=rank * ne)
     import ctypes as C
     from boxlcd_b200 import _lib
-    h_act = np.random.RandomState(rank).uniform(-1, 1, (ne, ve.A)).astype(np.float32)
+    # four host action batches cycled over the steps (each is page-locked once by blcd_step_host's buffer registry)
+    h_acts = [np.random.RandomState(4 * rank + i).uniform(-1, 1, (ne, ve.A)).astype(np.float32) for i in range(4)]
+    h_act = h_acts[0]
     h_fs = np.zeros((ne, ve.S), np.float32)
     h_bits = np.zeros((ne,) + ve.bits_shape(), np.uint32)
     h_done = np.zeros(ne, np.uint8)
-    Te = min(T, 20)
+    Te = T   # the same workload as the device-resident leg: a reset and one full episode of random actions
     def e2e_pass(k):
       ve.reset_dev()
-      for _ in range(k):
-        _lib.check(ve.l.blcd_step_host(ve.h, h_act.ctypes.data, h_fs.ctypes.data, h_bits.ctypes.data, h_done.ctypes.data))
-    e2e_pass(2)
+      for i in range(k):
+        _lib.check(ve.l.blcd_step_host(ve.h, h_acts[i % 4].ctypes.data, h_fs.ctypes.data, h_bits.ctypes.data, h_done.ctypes.data))
+    e2e_pass(4)
     barrier()
     t0 = time.perf_counter()
     e2e_pass(Te)
@@ -247,7 +249,7 @@ def main():
       dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     e2e = {'value': world_size * ne * Te / float(tt.item()), 'unit': 'env-steps/s', 'h2d_bytes_per_step': int(h_act.nbytes),
            'd2h_bytes_per_step': int(h_fs.nbytes + h_bits.nbytes + h_done.nbytes), 'worlds': ne, 'env_steps_timed': Te,
-           'api': 'blcd_step_host: host actions in, host full_state + packed frames + done out, one call per env step'}
+           'api': 'blcd_step_host: host actions in, host full_state + packed frames + done out, one call per env step; timed: reset + one full episode'}
 
   # ---- the rasterizer alone (blcd_render_poses): frames/s and HBM GB/s from poses resident in HBM -------------------------
   render = None

@@ -150,14 +150,15 @@ struct Sim {
   int oV, oP, oM, nbS;
   uint32_t live;  // lanes of this warp that own a world (for warp re-convergence points)
 
-  BLCD_HD Sim(const DScene& s, float* hot_base, uint32_t* state, int64_t n_worlds, int64_t world) : scene_host(&s) {
+  // world_end: one past the last world this LAUNCH covers (launches over a sub-range of the handle's worlds pass it)
+  BLCD_HD Sim(const DScene& s, float* hot_base, uint32_t* state, int64_t n_worlds, int64_t world, int64_t world_end = -1) : scene_host(&s) {
     hot.p = hot_base;
     oV = sc.h_vel; oP = sc.h_pos; oM = sc.h_mass; nbS = sc.nb;
 #ifdef __CUDA_ARCH__
     live = __activemask();
     {
       int64_t first = world - threadIdx.x;  // first world of this block
-      int64_t left = n_worlds - first;
+      int64_t left = (world_end < 0 ? n_worlds : world_end) - first;
       int warps = (int)((left + 31) / 32);
       int maxw = (int)(blockDim.x / 32);
       bar_threads = 32 * (warps < maxw ? warps : maxw);

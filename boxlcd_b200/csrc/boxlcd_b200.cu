@@ -198,12 +198,13 @@ __global__ void k_get_poses(const DScene* scene_g, const uint32_t* state, int64_
 
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 1 : 256 / BLOCK) k_step(const DScene* scene_g, uint32_t* state, int64_t n, uint64_t seed, int64_t world_offset,
-                                                 const float* actions, int n_steps, OutPtrs out) {
+                                                 const float* actions, int n_steps, OutPtrs out, int64_t w_begin, int64_t w_end) {
+  // worlds [w_begin, w_end) of the handle's n (blcd_step_host pipelines sub-ranges over several streams)
   unsigned char* smem_raw = blcd_smem;
   const DScene& sc = stage_scene<BLOCK>(scene_g, smem_raw);
-  int64_t w = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-  if (w >= n) return;
-  Sim<BLOCK> sim(sc, hot_base<BLOCK>(smem_raw), state, n, w);
+  int64_t w = w_begin + (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (w >= w_end) return;
+  Sim<BLOCK> sim(sc, hot_base<BLOCK>(smem_raw), state, n, w, w_end);
   sim.load(seed, world_offset + w);
   float act[kMaxObs];
   for (int t = 0; t < n_steps; ++t) {
@@ -348,6 +349,8 @@ __global__ void __launch_bounds__(kRenderThreads) k_render_poses(const DScene* s
 
 }  // namespace
 
+constexpr int kHostStreams = 8;
+
 struct BLCD_PENV {
   DScene scene;
   DScene* scene_dev = nullptr;
@@ -363,6 +366,7 @@ struct BLCD_PENV {
   float* h_act = nullptr; float* h_fs = nullptr; uint32_t* h_bits = nullptr; uint8_t* h_done = nullptr;
   float* d_act = nullptr; float* d_fs = nullptr; uint32_t* d_bits = nullptr; uint8_t* d_done = nullptr;
   std::vector<std::pair<const void*, size_t>> pinned;   // caller buffers page-locked by blcd_step_host
+  cudaStream_t hstream[kHostStreams] = {};              // blcd_step_host's pipeline streams
 };
 
 namespace {
@@ -466,6 +470,7 @@ int BLCD_P(destroy)(BLCD_PENV* h) {
   if (h->h_done) cudaFreeHost(h->h_done);
   cudaFree(h->d_act); cudaFree(h->d_fs); cudaFree(h->d_bits); cudaFree(h->d_done);
   for (auto& r : h->pinned) cudaHostUnregister(const_cast<void*>(r.first));
+  for (auto& st : h->hstream) if (st) cudaStreamDestroy(st);
   delete h;
   return 0;
 }
@@ -539,19 +544,23 @@ int BLCD_P(get_poses)(BLCD_PENV* h, float* poses_dev, uint32_t* variant_dev, uin
   return 0;
 }
 
-static int step_impl(BLCD_PENV* h, const float* actions_dev, int n_steps, OutPtrs out, cudaStream_t st) {
-  if (begin_timing(h, st)) return -1;
+static int step_range(BLCD_PENV* h, const float* actions_dev, int n_steps, OutPtrs out, cudaStream_t st, int64_t w_begin, int64_t w_end) {
   int rc = launch_sized(h, [&](auto B) {
     constexpr int BLOCK = decltype(B)::value;
-    k_step<BLOCK><<<(unsigned)((h->n + BLOCK - 1) / BLOCK), BLOCK, smem_bytes(h, BLOCK), st>>>(h->scene_dev, h->state, h->n, h->seed, h->world_offset,
-                                                                                               actions_dev, n_steps, out);
+    k_step<BLOCK><<<(unsigned)((w_end - w_begin + BLOCK - 1) / BLOCK), BLOCK, smem_bytes(h, BLOCK), st>>>(h->scene_dev, h->state, h->n, h->seed, h->world_offset,
+                                                                                                          actions_dev, n_steps, out, w_begin, w_end);
     return 0;
   });
   if (rc) return rc;
   CK(cudaGetLastError());
-  if (end_timing(h, st)) return -1;
   h->launches += 1;
   return 0;
+}
+
+static int step_impl(BLCD_PENV* h, const float* actions_dev, int n_steps, OutPtrs out, cudaStream_t st) {
+  if (begin_timing(h, st)) return -1;
+  if (step_range(h, actions_dev, n_steps, out, st, 0, h->n)) return -1;
+  return end_timing(h, st);
 }
 
 int BLCD_P(step)(BLCD_PENV* h, const float* actions_dev, float* actions_out_dev, uint64_t stream) {
@@ -631,19 +640,41 @@ int BLCD_P(step_host)(BLCD_PENV* h, const float* actions_host, float* full_state
     CK(cudaMalloc(&h->d_act, na)); CK(cudaMalloc(&h->d_fs, nf)); CK(cudaMalloc(&h->d_bits, nb)); CK(cudaMalloc(&h->d_done, nd));
     CK(cudaMallocHost(&h->h_act, na)); CK(cudaMallocHost(&h->h_fs, nf)); CK(cudaMallocHost(&h->h_bits, nb)); CK(cudaMallocHost(&h->h_done, nd));
   }
-  cudaStream_t st = 0;
   const bool pa = pin_user_buffer(h, actions_host, na), pf = pin_user_buffer(h, full_state_host, nf);
   const bool pb = pin_user_buffer(h, lcd_bits_host, nb), pd = pin_user_buffer(h, done_host, nd);
-  if (actions_host) {
-    if (!pa) memcpy(h->h_act, actions_host, na);
-    CK(cudaMemcpyAsync(h->d_act, pa ? actions_host : h->h_act, na, cudaMemcpyHostToDevice, st));
+  if (actions_host && !pa) memcpy(h->h_act, actions_host, na);
+  // Pipeline over sub-ranges of the worlds, one stream each: the copies of one range overlap the kernel of the next, and
+  // the ragged tail of one kernel (blocks finish at different times) is filled by the first blocks of the next.
+  // The streams are ordinary blocking streams, so everything here stays ordered after earlier work on the legacy
+  // default stream (reset, previous steps) and before later work on it.
+  int chunks = h->timing ? 1 : kHostStreams;
+  if (const char* e = getenv("BLCD_HOST_CHUNKS")) chunks = atoi(e);
+  const int64_t gran = 4 * (int64_t)h->block;   // chunk boundaries stay multiples of the block size
+  if (chunks < 1) chunks = 1;
+  if (chunks > kHostStreams) chunks = kHostStreams;
+  while (chunks > 1 && h->n / chunks < gran) --chunks;
+  for (int c = 0; c < chunks; ++c)
+    if (!h->hstream[c]) CK(cudaStreamCreate(&h->hstream[c]));
+  const int lw = row_words(sc.lcd_w);
+  const float* act_src = pa ? actions_host : h->h_act;
+  float* fs_dst = pf ? full_state_host : h->h_fs;
+  uint32_t* bits_dst = pb ? lcd_bits_host : h->h_bits;
+  uint8_t* done_dst = pd ? done_host : h->h_done;
+  if (chunks == 1 && begin_timing(h, h->hstream[0])) return -1;
+  for (int c = 0; c < chunks; ++c) {
+    const int64_t w0 = (h->n * c / chunks) / gran * gran, w1 = c + 1 == chunks ? h->n : (h->n * (c + 1) / chunks) / gran * gran;
+    if (w1 <= w0) continue;
+    cudaStream_t st = h->hstream[c];
+    const size_t cnt = (size_t)(w1 - w0);
+    if (actions_host) CK(cudaMemcpyAsync(h->d_act + w0 * sc.A, act_src + w0 * sc.A, cnt * sc.A * 4, cudaMemcpyHostToDevice, st));
+    OutPtrs out = {full_state_host ? h->d_fs : nullptr, nullptr, lcd_bits_host ? h->d_bits : nullptr, nullptr, done_host ? h->d_done : nullptr, nullptr};
+    if (step_range(h, actions_host ? h->d_act : nullptr, 1, out, st, w0, w1)) return -1;
+    if (full_state_host) CK(cudaMemcpyAsync(fs_dst + w0 * sc.S, h->d_fs + w0 * sc.S, cnt * sc.S * 4, cudaMemcpyDeviceToHost, st));
+    if (lcd_bits_host) CK(cudaMemcpyAsync(bits_dst + w0 * sc.lcd_h * lw, h->d_bits + w0 * sc.lcd_h * lw, cnt * sc.lcd_h * lw * 4, cudaMemcpyDeviceToHost, st));
+    if (done_host) CK(cudaMemcpyAsync(done_dst + w0, h->d_done + w0, cnt, cudaMemcpyDeviceToHost, st));
   }
-  OutPtrs out = {full_state_host ? h->d_fs : nullptr, nullptr, lcd_bits_host ? h->d_bits : nullptr, nullptr, done_host ? h->d_done : nullptr, nullptr};
-  if (step_impl(h, actions_host ? h->d_act : nullptr, 1, out, st)) return -1;
-  if (full_state_host) CK(cudaMemcpyAsync(pf ? full_state_host : h->h_fs, h->d_fs, nf, cudaMemcpyDeviceToHost, st));
-  if (lcd_bits_host) CK(cudaMemcpyAsync(pb ? lcd_bits_host : h->h_bits, h->d_bits, nb, cudaMemcpyDeviceToHost, st));
-  if (done_host) CK(cudaMemcpyAsync(pd ? done_host : h->h_done, h->d_done, nd, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  if (chunks == 1 && end_timing(h, h->hstream[0])) return -1;
+  for (int c = 0; c < chunks; ++c) CK(cudaStreamSynchronize(h->hstream[c]));
   if (full_state_host && !pf) memcpy(full_state_host, h->h_fs, nf);
   if (lcd_bits_host && !pb) memcpy(lcd_bits_host, h->h_bits, nb);
   if (done_host && !pd) memcpy(done_host, h->h_done, nd);

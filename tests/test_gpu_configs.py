@@ -217,3 +217,30 @@ def test_open_world_without_walls_matches_oracle_and_tracks_scroll():
   obs = e1.reset()
   x = (obs['full_state'][e1.obs_keys.index('urchin0:root:x:p')] + 1) / 2 * e1.WIDTH
   assert abs(e1.scroll - (x - e1.WIDTH / 2)) < 1e-6
+
+
+@pytest.mark.parametrize('n', [300, 5000, 20000])
+def test_host_buffer_step_pipeline_matches_device_path(n, monkeypatch):
+  """blcd_step_host (host actions in, host obs out; pipelined over world sub-ranges) == step_dev + observe_dev"""
+  import ctypes as C
+  env = make_env('UrchinBall')
+  act = np.random.RandomState(n).uniform(-1, 1, (n, env.act_size)).astype(np.float32)
+  p = lambda a: a.ctypes.data_as(C.c_void_p)
+  outs = []
+  for chunks in ('1', '4', '8'):
+    monkeypatch.setenv('BLCD_HOST_CHUNKS', chunks)
+    v = vec(env, n, seed=2)
+    v.reset_dev()
+    fs = np.zeros((n, v.S), np.float32); bits = np.zeros((n, v.H), np.uint32); dn = np.ones(n, np.uint8)
+    for _ in range(3):
+      assert v.l.blcd_step_host(v.h, p(act), p(fs), p(bits), p(dn)) == 0
+    outs.append((fs, bits, dn))
+    v.close()
+  v = vec(env, n, seed=2)
+  v.reset_dev()
+  for _ in range(3):
+    obs, _ = v.step_dev(torch.as_tensor(act).cuda())
+  ref = (obs['full_state'].cpu().numpy(), obs['lcd_bits'].cpu().numpy().view(np.uint32), obs['done'].cpu().numpy())
+  for o in outs:
+    for a, b in zip(o, ref):
+      assert (a == b).all()
