@@ -227,29 +227,48 @@ def main():
     ve = v if ne == n else VecWorldEnv(env, ne, device=dev, seed=0, world_offset=rank * ne)
     import ctypes as C
     from boxlcd_b200 import _lib
-    # four host action batches cycled over the steps (each is page-locked once by blcd_step_host's buffer registry)
-    h_acts = [np.random.RandomState(4 * rank + i).uniform(-1, 1, (ne, ve.A)).astype(np.float32) for i in range(4)]
+    # the same workload as the device-resident leg: a fresh U[-1, 1) action for every world and step (collect.py:35), drawn on
+    # the host beforehand; step t copies its own [N, A] slice host->device
+    h_acts = np.random.default_rng(rank).uniform(-1, 1, (max(T, 4), ne, ve.A)).astype(np.float32)
     h_act = h_acts[0]
+    ve.pin_host(h_acts)
     h_fs = np.zeros((ne, ve.S), np.float32)
     h_bits = np.zeros((ne,) + ve.bits_shape(), np.uint32)
     h_done = np.zeros(ne, np.uint8)
     Te = T   # the same workload as the device-resident leg: a reset and one full episode of random actions
+    # (a) one synchronous call per env step (AsyncVectorEnv.step call shape)
     def e2e_pass(k):
       ve.reset_dev()
       for i in range(k):
-        _lib.check(ve.l.blcd_step_host(ve.h, h_acts[i % 4].ctypes.data, h_fs.ctypes.data, h_bits.ctypes.data, h_done.ctypes.data))
-    e2e_pass(4)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_pass(Te)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    tt = torch.tensor([dt], device=dev, dtype=torch.float64)
-    if world_size > 1:
-      dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    e2e = {'value': world_size * ne * Te / float(tt.item()), 'unit': 'env-steps/s', 'h2d_bytes_per_step': int(h_act.nbytes),
+        _lib.check(ve.l.blcd_step_host(ve.h, h_acts[i].ctypes.data, h_fs.ctypes.data, h_bits.ctypes.data, h_done.ctypes.data))
+    # (b) step_async / step_wait call shape with two steps in flight: a collector's actions do not depend on the step just
+    # submitted (collect.py:35), so the copies and the kernel tail of step t hide behind the kernel of step t+1.  Every
+    # step still moves its own actions host->device and its own observations device->host; four output slots are cycled.
+    ring = [(np.zeros_like(h_fs), np.zeros_like(h_bits), np.zeros_like(h_done)) for _ in range(4)]
+    ve.pin_host(*[b for r in ring for b in r])
+    def e2e_pass_async(k):
+      ve.reset_dev()
+      for i in range(k):
+        f, b, d = ring[i % 4]
+        ve.step_host_async(h_acts[i], f, b, d)
+        ve.step_host_wait(keep_in_flight=2)
+      ve.step_host_wait(0)
+    def timed(fn):
+      fn(4)
+      barrier()
+      t0 = time.perf_counter()
+      fn(Te)
+      torch.cuda.synchronize()
+      tt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+      if world_size > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+      return world_size * ne * Te / float(tt.item())
+    e_sync, e_async = timed(e2e_pass), timed(e2e_pass_async)
+    e2e = {'value': e_sync, 'unit': 'env-steps/s', 'h2d_bytes_per_step': int(h_act.nbytes),
            'd2h_bytes_per_step': int(h_fs.nbytes + h_bits.nbytes + h_done.nbytes), 'worlds': ne, 'env_steps_timed': Te,
-           'api': 'blcd_step_host: host actions in, host full_state + packed frames + done out, one call per env step; timed: reset + one full episode'}
+           'api': 'blcd_step_host: host actions in, host full_state + packed frames + done out, one blocking call per env step; '
+                  'timed: reset + one full episode of fresh random actions',
+           'pipelined_value': e_async, 'pipelined_api': 'blcd_step_host_async + blcd_step_host_wait(keep_in_flight=2), same copies per step'}
 
   # ---- the rasterizer alone (blcd_render_poses): frames/s and HBM GB/s from poses resident in HBM -------------------------
   render = None

@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, 'csrc')
 _lib = None
 
 SYMBOLS = ['blcd_last_error', 'blcd_version', 'blcd_create', 'blcd_destroy', 'blcd_reset', 'blcd_step', 'blcd_step_observe', 'blcd_observe',
-           'blcd_rollout', 'blcd_step_host', 'blcd_render_poses', 'blcd_render_poses_sized', 'blcd_set_bodies', 'blcd_get_bodies', 'blcd_get_poses', 'blcd_check_finite',
+           'blcd_rollout', 'blcd_step_host', 'blcd_pin_host', 'blcd_step_host_async', 'blcd_step_host_wait', 'blcd_render_poses', 'blcd_render_poses_sized', 'blcd_set_bodies', 'blcd_get_bodies', 'blcd_get_poses', 'blcd_check_finite',
            'blcd_state_bytes', 'blcd_save_state', 'blcd_load_state', 'blcd_num_worlds', 'blcd_kernel_launches', 'blcd_last_step_ms',
            'blcd_enable_timing', 'blcd_get_counters', 'blcd_scene_info']
 
@@ -42,6 +42,9 @@ def lib():
   l.blcd_observe.argtypes = [vp, vp, vp, vp, vp, vp, u64]
   l.blcd_rollout.argtypes = [vp, i32, vp, vp, vp, u64]
   l.blcd_step_host.argtypes = [vp, vp, vp, vp, vp]
+  l.blcd_pin_host.argtypes = [vp, vp, i64]
+  l.blcd_step_host_async.argtypes = [vp, vp, vp, vp, vp]
+  l.blcd_step_host_wait.argtypes = [vp, i32]
   l.blcd_render_poses.argtypes = [vp, vp, vp, i64, vp, u64]
   l.blcd_render_poses_sized.argtypes = [vp, vp, vp, i64, i32, i32, vp, u64]
   l.blcd_set_bodies.argtypes = [vp, vp, vp, u64]

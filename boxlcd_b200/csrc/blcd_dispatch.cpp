@@ -90,6 +90,18 @@ int blcd_step_host(blcd_handle h, const float* actions_host, float* full_state_h
   BLCD_NEED(h, "blcd_step_host");
   return BLCD_FWD(step_host, actions_host, full_state_host, lcd_bits_host, done_host);
 }
+int blcd_pin_host(blcd_handle h, const void* buf_host, int64_t bytes) {
+  BLCD_NEED(h, "blcd_pin_host");
+  return BLCD_FWD(pin_host, buf_host, bytes);
+}
+int blcd_step_host_async(blcd_handle h, const float* actions_host, float* full_state_host, uint32_t* lcd_bits_host, uint8_t* done_host) {
+  BLCD_NEED(h, "blcd_step_host_async");
+  return BLCD_FWD(step_host_async, actions_host, full_state_host, lcd_bits_host, done_host);
+}
+int blcd_step_host_wait(blcd_handle h, int32_t keep_in_flight) {
+  BLCD_NEED(h, "blcd_step_host_wait");
+  return BLCD_FWD(step_host_wait, keep_in_flight);
+}
 int blcd_render_poses(blcd_handle h, const float* poses_dev, const uint32_t* variant_dev, int64_t n, uint32_t* lcd_bits_dev, uint64_t stream) {
   BLCD_NEED(h, "blcd_render_poses");
   return BLCD_FWD(render_poses, poses_dev, variant_dev, n, lcd_bits_dev, stream);

@@ -21,6 +21,9 @@ int BLCD_P(step_observe)(BLCD_PENV* h, const float* actions_dev, float* actions_
                          uint32_t* lcd_bits_dev, uint8_t* lcd_bool_dev, uint8_t* done_dev, uint64_t stream);
 int BLCD_P(rollout)(BLCD_PENV* h, int32_t T, float* full_state_dev, uint32_t* lcd_bits_dev, float* actions_dev, uint64_t stream);
 int BLCD_P(step_host)(BLCD_PENV* h, const float* actions_host, float* full_state_host, uint32_t* lcd_bits_host, uint8_t* done_host);
+int BLCD_P(pin_host)(BLCD_PENV* h, const void* buf_host, int64_t bytes);
+int BLCD_P(step_host_async)(BLCD_PENV* h, const float* actions_host, float* full_state_host, uint32_t* lcd_bits_host, uint8_t* done_host);
+int BLCD_P(step_host_wait)(BLCD_PENV* h, int32_t keep_in_flight);
 int BLCD_P(render_poses)(BLCD_PENV* h, const float* poses_dev, const uint32_t* variant_dev, int64_t n, uint32_t* lcd_bits_dev, uint64_t stream);
 int BLCD_P(render_poses_sized)(BLCD_PENV* h, const float* poses_dev, const uint32_t* variant_dev, int64_t n, int32_t lcd_w, int32_t lcd_h,
                                uint32_t* lcd_bits_dev, uint64_t stream);

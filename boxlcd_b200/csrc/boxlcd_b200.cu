@@ -350,6 +350,7 @@ __global__ void __launch_bounds__(kRenderThreads) k_render_poses(const DScene* s
 }  // namespace
 
 constexpr int kHostStreams = 8;
+constexpr int kHostDepth = 4;     // host steps that may be in flight (blcd_step_host_async)
 
 struct BLCD_PENV {
   DScene scene;
@@ -366,7 +367,11 @@ struct BLCD_PENV {
   float* h_act = nullptr; float* h_fs = nullptr; uint32_t* h_bits = nullptr; uint8_t* h_done = nullptr;
   float* d_act = nullptr; float* d_fs = nullptr; uint32_t* d_bits = nullptr; uint8_t* d_done = nullptr;
   std::vector<std::pair<const void*, size_t>> pinned;   // caller buffers page-locked by blcd_step_host
+  std::vector<std::pair<const void*, size_t>> pinned_user;   // ... and by blcd_pin_host
   cudaStream_t hstream[kHostStreams] = {};              // blcd_step_host's pipeline streams
+  cudaEvent_t hev[kHostDepth][kHostStreams] = {};       // completion of host step s (ring) on each stream
+  uint64_t host_submitted = 0, host_completed = 0;
+  int host_chunks = 0;
 };
 
 namespace {
@@ -460,6 +465,7 @@ int BLCD_P(create)(const blcd_spec* spec_host, int64_t n_worlds, int device, uin
 int BLCD_P(destroy)(BLCD_PENV* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
+  for (auto& st : h->hstream) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }   // nothing in flight past here
   cudaFree(h->scene_dev);
   cudaFree(h->state);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -470,7 +476,8 @@ int BLCD_P(destroy)(BLCD_PENV* h) {
   if (h->h_done) cudaFreeHost(h->h_done);
   cudaFree(h->d_act); cudaFree(h->d_fs); cudaFree(h->d_bits); cudaFree(h->d_done);
   for (auto& r : h->pinned) cudaHostUnregister(const_cast<void*>(r.first));
-  for (auto& st : h->hstream) if (st) cudaStreamDestroy(st);
+  for (auto& r : h->pinned_user) cudaHostUnregister(const_cast<void*>(r.first));
+  for (auto& ring : h->hev) for (auto& e : ring) if (e) cudaEventDestroy(e);
   delete h;
   return 0;
 }
@@ -615,15 +622,28 @@ int BLCD_P(rollout)(BLCD_PENV* h, int32_t T, float* full_state_dev, uint32_t* lc
 
 // pin a caller-owned host buffer once (page-locks it in place) so that later copies are direct DMA transfers; returns
 // false if the driver refuses (then the call falls back to the handle's own pinned staging buffers)
-static bool pin_user_buffer(BLCD_PENV* h, const void* p, size_t bytes) {
+static bool is_pinned(const BLCD_PENV* h, const void* p, size_t bytes) {
+  const char* q = static_cast<const char*>(p);
+  for (const auto* list : {&h->pinned, &h->pinned_user})
+    for (auto& r : *list) {
+      const char* base = static_cast<const char*>(r.first);
+      if (q >= base && q + bytes <= base + r.second) return true;
+    }
+  return false;
+}
+
+// keep = true: pinned on the caller's request (blcd_pin_host), stays until blcd_destroy; false: pinned on first use by
+// blcd_step_host, kept in a small most-recent list
+static bool pin_user_buffer(BLCD_PENV* h, const void* p, size_t bytes, bool keep = false) {
   if (!p) return false;
-  for (auto& r : h->pinned)
-    if (r.first == p && r.second >= bytes) return true;
+  if (is_pinned(h, p, bytes)) return true;
   if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) != cudaSuccess) {
     cudaGetLastError();
     return false;
   }
-  if (h->pinned.size() >= 8) {   // keep the registry small: forget (and unpin) the oldest buffer
+  if (keep) { h->pinned_user.emplace_back(p, bytes); return true; }
+  if (h->pinned.size() >= 8) {   // keep the registry small: forget (and unpin) the oldest buffer -- once nothing is in flight
+    for (auto& st : h->hstream) if (st) cudaStreamSynchronize(st);
     cudaHostUnregister(const_cast<void*>(h->pinned.front().first));
     h->pinned.erase(h->pinned.begin());
   }
@@ -631,54 +651,120 @@ static bool pin_user_buffer(BLCD_PENV* h, const void* p, size_t bytes) {
   return true;
 }
 
-int BLCD_P(step_host)(BLCD_PENV* h, const float* actions_host, float* full_state_host, uint32_t* lcd_bits_host, uint8_t* done_host) {
-  if (!h) return fail("blcd_step_host: null handle");
-  CK(cudaSetDevice(h->device));
+// Enqueue one env step through host buffers on the handle's pipeline streams.  The worlds are split into sub-ranges, one
+// stream each: the copies of one range overlap the kernel of the next, and the ragged tail of one kernel (blocks finish
+// at different times) is filled by the first blocks of the next -- also across consecutive steps, because range c of
+// step t+1 only waits for range c of step t.  The streams are ordinary blocking streams, so everything stays ordered
+// after earlier work on the legacy default stream (reset, device-side steps) and before later work on it.
+// src / dst: page-locked memory the copies read from / write to (the caller's buffers, or the handle's staging area).
+static int host_step_submit(BLCD_PENV* h, const float* act_src, float* fs_dst, uint32_t* bits_dst, uint8_t* done_dst, int chunks) {
   const DScene& sc = h->scene;
-  size_t na = (size_t)h->n * sc.A * 4, nf = (size_t)h->n * sc.S * 4, nb = (size_t)h->n * sc.lcd_h * row_words(sc.lcd_w) * 4, nd = (size_t)h->n;
-  if (!h->d_act) {
-    CK(cudaMalloc(&h->d_act, na)); CK(cudaMalloc(&h->d_fs, nf)); CK(cudaMalloc(&h->d_bits, nb)); CK(cudaMalloc(&h->d_done, nd));
-    CK(cudaMallocHost(&h->h_act, na)); CK(cudaMallocHost(&h->h_fs, nf)); CK(cudaMallocHost(&h->h_bits, nb)); CK(cudaMallocHost(&h->h_done, nd));
-  }
-  const bool pa = pin_user_buffer(h, actions_host, na), pf = pin_user_buffer(h, full_state_host, nf);
-  const bool pb = pin_user_buffer(h, lcd_bits_host, nb), pd = pin_user_buffer(h, done_host, nd);
-  if (actions_host && !pa) memcpy(h->h_act, actions_host, na);
-  // Pipeline over sub-ranges of the worlds, one stream each: the copies of one range overlap the kernel of the next, and
-  // the ragged tail of one kernel (blocks finish at different times) is filled by the first blocks of the next.
-  // The streams are ordinary blocking streams, so everything here stays ordered after earlier work on the legacy
-  // default stream (reset, previous steps) and before later work on it.
-  int chunks = h->timing ? 1 : kHostStreams;
-  if (const char* e = getenv("BLCD_HOST_CHUNKS")) chunks = atoi(e);
-  const int64_t gran = 4 * (int64_t)h->block;   // chunk boundaries stay multiples of the block size
+  const int64_t gran = 4 * (int64_t)h->block;   // range boundaries stay multiples of the block size
   if (chunks < 1) chunks = 1;
   if (chunks > kHostStreams) chunks = kHostStreams;
   while (chunks > 1 && h->n / chunks < gran) --chunks;
+  if (h->host_chunks && h->host_chunks != chunks && h->host_submitted != h->host_completed)
+    return fail("blcd_step_host: the number of pipeline ranges cannot change while steps are in flight");
+  h->host_chunks = chunks;
   for (int c = 0; c < chunks; ++c)
     if (!h->hstream[c]) CK(cudaStreamCreate(&h->hstream[c]));
   const int lw = row_words(sc.lcd_w);
-  const float* act_src = pa ? actions_host : h->h_act;
-  float* fs_dst = pf ? full_state_host : h->h_fs;
-  uint32_t* bits_dst = pb ? lcd_bits_host : h->h_bits;
-  uint8_t* done_dst = pd ? done_host : h->h_done;
+  const int slot = (int)(h->host_submitted % kHostDepth);
   if (chunks == 1 && begin_timing(h, h->hstream[0])) return -1;
   for (int c = 0; c < chunks; ++c) {
     const int64_t w0 = (h->n * c / chunks) / gran * gran, w1 = c + 1 == chunks ? h->n : (h->n * (c + 1) / chunks) / gran * gran;
-    if (w1 <= w0) continue;
     cudaStream_t st = h->hstream[c];
-    const size_t cnt = (size_t)(w1 - w0);
-    if (actions_host) CK(cudaMemcpyAsync(h->d_act + w0 * sc.A, act_src + w0 * sc.A, cnt * sc.A * 4, cudaMemcpyHostToDevice, st));
-    OutPtrs out = {full_state_host ? h->d_fs : nullptr, nullptr, lcd_bits_host ? h->d_bits : nullptr, nullptr, done_host ? h->d_done : nullptr, nullptr};
-    if (step_range(h, actions_host ? h->d_act : nullptr, 1, out, st, w0, w1)) return -1;
-    if (full_state_host) CK(cudaMemcpyAsync(fs_dst + w0 * sc.S, h->d_fs + w0 * sc.S, cnt * sc.S * 4, cudaMemcpyDeviceToHost, st));
-    if (lcd_bits_host) CK(cudaMemcpyAsync(bits_dst + w0 * sc.lcd_h * lw, h->d_bits + w0 * sc.lcd_h * lw, cnt * sc.lcd_h * lw * 4, cudaMemcpyDeviceToHost, st));
-    if (done_host) CK(cudaMemcpyAsync(done_dst + w0, h->d_done + w0, cnt, cudaMemcpyDeviceToHost, st));
+    if (w1 > w0) {
+      const size_t cnt = (size_t)(w1 - w0);
+      if (act_src) CK(cudaMemcpyAsync(h->d_act + w0 * sc.A, act_src + w0 * sc.A, cnt * sc.A * 4, cudaMemcpyHostToDevice, st));
+      OutPtrs out = {fs_dst ? h->d_fs : nullptr, nullptr, bits_dst ? h->d_bits : nullptr, nullptr, done_dst ? h->d_done : nullptr, nullptr};
+      if (step_range(h, act_src ? h->d_act : nullptr, 1, out, st, w0, w1)) return -1;
+      if (fs_dst) CK(cudaMemcpyAsync(fs_dst + w0 * sc.S, h->d_fs + w0 * sc.S, cnt * sc.S * 4, cudaMemcpyDeviceToHost, st));
+      if (bits_dst) CK(cudaMemcpyAsync(bits_dst + w0 * sc.lcd_h * lw, h->d_bits + w0 * sc.lcd_h * lw, cnt * sc.lcd_h * lw * 4, cudaMemcpyDeviceToHost, st));
+      if (done_dst) CK(cudaMemcpyAsync(done_dst + w0, h->d_done + w0, cnt, cudaMemcpyDeviceToHost, st));
+    }
+    if (!h->hev[slot][c]) CK(cudaEventCreateWithFlags(&h->hev[slot][c], cudaEventDisableTiming));
+    CK(cudaEventRecord(h->hev[slot][c], st));
   }
   if (chunks == 1 && end_timing(h, h->hstream[0])) return -1;
-  for (int c = 0; c < chunks; ++c) CK(cudaStreamSynchronize(h->hstream[c]));
+  h->host_submitted += 1;
+  return 0;
+}
+
+// block until at most `keep` submitted host steps are still in flight
+static int host_step_wait(BLCD_PENV* h, int keep) {
+  if (keep < 0) keep = 0;
+  while (h->host_submitted - h->host_completed > (uint64_t)keep) {
+    const int slot = (int)(h->host_completed % kHostDepth);
+    for (int c = 0; c < h->host_chunks; ++c) CK(cudaEventSynchronize(h->hev[slot][c]));
+    h->host_completed += 1;
+  }
+  return 0;
+}
+
+static int host_step_buffers(BLCD_PENV* h, size_t* na, size_t* nf, size_t* nb, size_t* nd) {
+  const DScene& sc = h->scene;
+  *na = (size_t)h->n * sc.A * 4; *nf = (size_t)h->n * sc.S * 4; *nb = (size_t)h->n * sc.lcd_h * row_words(sc.lcd_w) * 4; *nd = (size_t)h->n;
+  if (!h->d_act) {
+    CK(cudaMalloc(&h->d_act, *na)); CK(cudaMalloc(&h->d_fs, *nf)); CK(cudaMalloc(&h->d_bits, *nb)); CK(cudaMalloc(&h->d_done, *nd));
+    CK(cudaMallocHost(&h->h_act, *na)); CK(cudaMallocHost(&h->h_fs, *nf)); CK(cudaMallocHost(&h->h_bits, *nb)); CK(cudaMallocHost(&h->h_done, *nd));
+  }
+  return 0;
+}
+
+static int host_chunks_default(const BLCD_PENV* h) {
+  int chunks = h->timing ? 1 : kHostStreams;
+  if (const char* e = getenv("BLCD_HOST_CHUNKS")) chunks = atoi(e);
+  return chunks;
+}
+
+int BLCD_P(step_host)(BLCD_PENV* h, const float* actions_host, float* full_state_host, uint32_t* lcd_bits_host, uint8_t* done_host) {
+  if (!h) return fail("blcd_step_host: null handle");
+  CK(cudaSetDevice(h->device));
+  size_t na, nf, nb, nd;
+  if (host_step_buffers(h, &na, &nf, &nb, &nd)) return -1;
+  if (host_step_wait(h, 0)) return -1;   // earlier asynchronous steps first: the device-side staging area is shared
+  // caller buffers are page-locked in place once (then the copies are direct DMA transfers); if the driver refuses, the
+  // call goes through the handle's own pinned staging buffers
+  const bool pa = pin_user_buffer(h, actions_host, na), pf = pin_user_buffer(h, full_state_host, nf);
+  const bool pb = pin_user_buffer(h, lcd_bits_host, nb), pd = pin_user_buffer(h, done_host, nd);
+  if (actions_host && !pa) memcpy(h->h_act, actions_host, na);
+  if (host_step_submit(h, actions_host ? (pa ? actions_host : h->h_act) : nullptr, full_state_host ? (pf ? full_state_host : h->h_fs) : nullptr,
+                       lcd_bits_host ? (pb ? lcd_bits_host : h->h_bits) : nullptr, done_host ? (pd ? done_host : h->h_done) : nullptr,
+                       host_chunks_default(h)))
+    return -1;
+  if (host_step_wait(h, 0)) return -1;
   if (full_state_host && !pf) memcpy(full_state_host, h->h_fs, nf);
   if (lcd_bits_host && !pb) memcpy(lcd_bits_host, h->h_bits, nb);
   if (done_host && !pd) memcpy(done_host, h->h_done, nd);
   return 0;
+}
+
+int BLCD_P(pin_host)(BLCD_PENV* h, const void* buf_host, int64_t bytes) {
+  if (!h || !buf_host || bytes <= 0) return fail("blcd_pin_host: bad arguments");
+  CK(cudaSetDevice(h->device));
+  if (!pin_user_buffer(h, buf_host, (size_t)bytes, true)) return fail("blcd_pin_host: the driver refused to page-lock this buffer");
+  return 0;
+}
+
+int BLCD_P(step_host_async)(BLCD_PENV* h, const float* actions_host, float* full_state_host, uint32_t* lcd_bits_host, uint8_t* done_host) {
+  if (!h) return fail("blcd_step_host_async: null handle");
+  CK(cudaSetDevice(h->device));
+  size_t na, nf, nb, nd;
+  if (host_step_buffers(h, &na, &nf, &nb, &nd)) return -1;
+  if ((actions_host && !is_pinned(h, actions_host, na)) || (full_state_host && !is_pinned(h, full_state_host, nf)) ||
+      (lcd_bits_host && !is_pinned(h, lcd_bits_host, nb)) || (done_host && !is_pinned(h, done_host, nd)))
+    return fail("blcd_step_host_async: every buffer must lie inside memory page-locked with blcd_pin_host");
+  // the device-side staging area is single-buffered per world range: range c of this step runs after range c of the
+  // previous step on the same stream, so its copies are ordered; bound the queue by the event ring
+  if (host_step_wait(h, kHostDepth - 1)) return -1;
+  return host_step_submit(h, actions_host, full_state_host, lcd_bits_host, done_host, host_chunks_default(h));
+}
+
+int BLCD_P(step_host_wait)(BLCD_PENV* h, int32_t keep_in_flight) {
+  if (!h) return fail("blcd_step_host_wait: null handle");
+  CK(cudaSetDevice(h->device));
+  return host_step_wait(h, keep_in_flight);
 }
 
 int BLCD_P(render_poses)(BLCD_PENV* h, const float* poses_dev, const uint32_t* variant_dev, int64_t n, uint32_t* lcd_bits_dev, uint64_t stream) {

@@ -103,6 +103,26 @@ class VecWorldEnv:
     _lib.check(self.l.blcd_render_poses_sized(self.h, _ptr(poses), _ptr(variants), n, width, height, _ptr(out), self._stream()))
     return out
 
+  # -- host-buffer stepping (the C ABI's reference-facing entry points) ------------------------------------------------
+  def pin_host(self, *arrays):
+    """page-lock numpy arrays once so that step_host_async can copy straight from / into them (or slices of them)"""
+    for a in arrays:
+      _lib.check(self.l.blcd_pin_host(self.h, a.ctypes.data, a.nbytes))
+
+  def step_host(self, actions, full_state=None, lcd_bits=None, done=None):
+    """one env step: numpy actions [N, A] f32 in, numpy full_state [N, S] f32 / packed frames / done [N] u8 out (synchronous)"""
+    p = lambda a: None if a is None else a.ctypes.data
+    _lib.check(self.l.blcd_step_host(self.h, p(actions), p(full_state), p(lcd_bits), p(done)))
+
+  def step_host_async(self, actions, full_state=None, lcd_bits=None, done=None):
+    """AsyncVectorEnv.step_async with host buffers (all inside memory given to pin_host); returns immediately"""
+    p = lambda a: None if a is None else a.ctypes.data
+    _lib.check(self.l.blcd_step_host_async(self.h, p(actions), p(full_state), p(lcd_bits), p(done)))
+
+  def step_host_wait(self, keep_in_flight=0):
+    """AsyncVectorEnv.step_wait: block until at most `keep_in_flight` submitted steps are unfinished"""
+    _lib.check(self.l.blcd_step_host_wait(self.h, int(keep_in_flight)))
+
   def set_bodies(self, bodies, variants=None):
     b = torch.as_tensor(np.ascontiguousarray(bodies, np.float32)).to(self.device)
     v = None if variants is None else torch.as_tensor(np.ascontiguousarray(variants, np.uint32).view(np.int32)).to(self.device)

@@ -158,6 +158,20 @@ int blcd_rollout(blcd_handle h, int32_t T, float* full_state_dev, uint32_t* lcd_
  * host->device, steps, observes, copies full_state and packed frames device->host, and synchronizes. */
 int blcd_step_host(blcd_handle h, const float* actions_host, float* full_state_host, uint32_t* lcd_bits_host, uint8_t* done_host);
 
+/* The same split into submit and wait, the call shape of the reference's AsyncVectorEnv.step_async / step_wait
+ * (research/wrappers/async_vector_env.py:131-242), for callers whose next actions do not depend on the step just
+ * submitted (collect.py:35 samples actions independently of the observation; double-buffered RL):
+ *   blcd_pin_host         page-locks caller memory once (a whole [T, N, ...] dataset array, or a ring of step buffers);
+ *   blcd_step_host_async  enqueues one env step reading / writing buffers inside pinned memory and returns at once
+ *                         (up to 3 further steps may be queued behind it; it blocks only when that queue is full);
+ *   blcd_step_host_wait   returns when at most keep_in_flight submitted steps are unfinished; the outputs of every
+ *                         finished step are then complete in host memory.  Steps finish in submission order.
+ * Each step still copies its actions host->device and its observations device->host; consecutive steps overlap only in
+ * that the copies and the ragged kernel tail of one step hide behind the next step's kernel. */
+int blcd_pin_host(blcd_handle h, const void* buf_host, int64_t bytes);
+int blcd_step_host_async(blcd_handle h, const float* actions_host, float* full_state_host, uint32_t* lcd_bits_host, uint8_t* done_host);
+int blcd_step_host_wait(blcd_handle h, int32_t keep_in_flight);
+
 /* lcd_render() from explicit poses, no simulation state involved: poses_dev [N, n_bodies, 4] = (x, y, sin, cos) float32
  * of every dynamic body's b2Transform; variant_dev optional [N] uint32 bitmask selecting shape variant per body. */
 int blcd_render_poses(blcd_handle h, const float* poses_dev, const uint32_t* variant_dev, int64_t n, uint32_t* lcd_bits_dev, uint64_t stream);

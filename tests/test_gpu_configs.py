@@ -244,3 +244,29 @@ def test_host_buffer_step_pipeline_matches_device_path(n, monkeypatch):
   for o in outs:
     for a, b in zip(o, ref):
       assert (a == b).all()
+
+
+def test_async_host_steps_match_synchronous_steps():
+  """blcd_step_host_async / _wait (AsyncVectorEnv.step_async / step_wait call shape): a [T, N, ...] dataset filled with up to
+  three steps in flight equals the same steps taken one synchronous call at a time"""
+  env = make_env('LuxoCube')
+  n, T = 6000, 12
+  acts = np.random.RandomState(0).uniform(-1, 1, (T, n, env.act_size)).astype(np.float32)
+  v = vec(env, n, seed=5)
+  fs = np.zeros((T, n, v.S), np.float32); bits = np.zeros((T, n, v.H), np.uint32); dn = np.zeros((T, n), np.uint8)
+  with pytest.raises(RuntimeError, match='page-locked'):
+    v.step_host_async(acts[0], fs[0], bits[0], dn[0])
+  v.pin_host(acts, fs, bits, dn)
+  v.reset_dev()
+  for t in range(T):
+    v.step_host_async(acts[t], fs[t], bits[t], dn[t])
+    v.step_host_wait(keep_in_flight=2)
+  v.step_host_wait()
+  v2 = vec(env, n, seed=5)
+  v2.reset_dev()
+  fs2 = np.zeros((n, v.S), np.float32); bits2 = np.zeros((n, v.H), np.uint32); dn2 = np.zeros(n, np.uint8)
+  for t in range(T):
+    v2.step_host(acts[t], fs2, bits2, dn2)
+    assert (fs[t] == fs2).all() and (bits[t] == bits2).all() and (dn[t] == dn2).all(), t
+  # device-side calls issued afterwards see the state after all T steps
+  assert (v.observe()['full_state'] == fs[-1]).all()
