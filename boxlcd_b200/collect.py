@@ -4,7 +4,8 @@
   python -m boxlcd_b200.collect --env=Urchin --barrels=10 --logdir=logs/  -> logs/{train}/{timestamp}-{ep_len}.barrel.npz
 
 Replaces the loops of examples/collect.py:24-41 and research/data.py:36-79: every rollout is one world of a batched
-fused kernel launch (blcd_rollout: on-device action RNG -> step -> obs -> frame); the host only reshapes and writes.
+fused kernel launch (blcd_rollout: on-device action RNG -> step -> obs -> frame); the host only reshapes and writes
+(npz_writer.py: the same .npz container, deflated on all host cores instead of one).
 File formats are the reference's: `action` float64 [N, T, A], `full_state` float32 [N, T, S], `proprio` float32
 [N, T, P], `lcd` bool [N, T, H, W]; element [i, j] is the observation BEFORE action j; no resets inside a rollout.
 With several GPUs (torchrun) each rank collects a contiguous shard of rollouts; npz mode gathers the shards on rank 0
@@ -18,6 +19,7 @@ import time
 from datetime import datetime
 
 import numpy as np
+from boxlcd_b200.npz_writer import savez_compressed_parallel
 
 BARREL_SIZE = 1000  # research/data.py:21
 
@@ -123,7 +125,7 @@ def main(argv=None):
     for bi in range(rank, G.barrels, world):
       data = collect_arrays(env, BARREL_SIZE, T, min(G.batch, BARREL_SIZE), G.seed, world_offset=bi * BARREL_SIZE, progress=say)
       stamp = datetime.now().strftime('%Y%m%dT%H%M%S') + (f'r{rank}b{bi}' if world > 1 or G.barrels > 1 else '')
-      np.savez_compressed(logdir / f'{stamp}-{T}.barrel', **data)
+      savez_compressed_parallel(logdir / f'{stamp}-{T}.barrel', **data)
   else:
     N = G.collect_n
     lo, hi = shard_range(N, rank, world)
@@ -131,7 +133,7 @@ def main(argv=None):
     data = gather_shards(data, rank, world)
     if rank == 0:
       os.makedirs('rollouts', exist_ok=True)
-      np.savez_compressed(f'rollouts/{G.env}-{N}.npz', **data)
+      savez_compressed_parallel(f'rollouts/{G.env}-{N}.npz', **data)
       print(f'\nwrote rollouts/{G.env}-{N}.npz')
   if world > 1:
     import torch.distributed as dist
