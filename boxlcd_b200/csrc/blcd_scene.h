@@ -13,7 +13,7 @@ namespace BLCD_NS {
 enum { SH_CIRCLE = 0, SH_EDGE = 1, SH_POLY = 2 };
 constexpr int kSlotWords = 16;   // one persistent manifold slot
 constexpr int kBodyWords = 13;   // cx cy a vx vy w sleepTime fat(lo.x lo.y hi.x hi.y) px py (b2Body::m_xf.p)
-constexpr int kJointWords = 6;   // impulse xyz, motorImpulse, motorSpeed, limitState
+constexpr int kJointWords = 7;   // impulse xyz, motorImpulse, motorSpeed, limitState, referenceAngle
 // misc words: flags, inv_dt0, ep_t, rng draws [, shape variants].  With at most 8 bodies the flag word holds the awake
 // bits (0..7), the shape-variant bits (8..15) and e_newFixture (16); the large profile keeps the variants in a word of
 // their own.
@@ -81,7 +81,7 @@ struct DScene {
 };
 
 // hot (shared-memory) record sizes
-constexpr int kHotJoint = 17;        // rA rB K(6) motorMass impulse(3) motorImpulse motorSpeed packed
+constexpr int kHotJoint = 18;        // rA rB K(6) motorMass impulse(3) motorImpulse motorSpeed packed referenceAngle
 constexpr int kHotConHdr = 10;       // normal(2) friction packed K(3) normalMass(3)
 constexpr int kHotConPt = 9;         // rA rB normalMass tangentMass bias ni ti
 constexpr int kHotCon = kHotConHdr + 2 * kHotConPt;

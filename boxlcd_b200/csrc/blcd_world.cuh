@@ -84,7 +84,7 @@ struct Philox {
 };
 
 // joint record in shared memory
-enum { J_RAX = 0, J_RAY, J_RBX, J_RBY, J_EXX, J_EYX, J_EZX, J_EYY, J_EZY, J_EZZ, J_MM, J_IX, J_IY, J_IZ, J_MI, J_MS, J_PK };
+enum { J_RAX = 0, J_RAY, J_RBX, J_RBY, J_EXX, J_EYX, J_EZX, J_EYY, J_EZY, J_EZZ, J_MM, J_IX, J_IY, J_IZ, J_MI, J_MS, J_PK, J_REF };
 // contact record in shared memory
 // C_PK packs: body row A (bits 0..4), row B (5..9), point count (10..11), manifold slot (12..19), island (20..)
 enum { C_NX = 0, C_NY, C_FR, C_PK, C_K11, C_K12, C_K22, C_N11, C_N12, C_N22, C_PT };
@@ -261,6 +261,7 @@ struct Sim {
       jr[h + J_IX] = g.f(o + 0); jr[h + J_IY] = g.f(o + 1); jr[h + J_IZ] = g.f(o + 2);
       jr[h + J_MI] = g.f(o + 3); jr[h + J_MS] = g.f(o + 4);
       jru(h + J_PK) = g.u(o + 5) & 3u;  // limit state; solve-order fields are filled per sub-step
+      jr[h + J_REF] = g.f(o + 6);
     }
     ncl = (int)g.u(sc.off_clist);
     for (int k = 0; k < kMaxPairs; ++k) pslot[k] = -1;
@@ -300,6 +301,7 @@ struct Sim {
       g.f(o + 0) = jr[h + J_IX]; g.f(o + 1) = jr[h + J_IY]; g.f(o + 2) = jr[h + J_IZ];
       g.f(o + 3) = jr[h + J_MI]; g.f(o + 4) = jr[h + J_MS];
       g.u(o + 5) = jru(h + J_PK) & 3u;
+      g.f(o + 6) = jr[h + J_REF];
     }
     g.u(sc.off_clist) = (uint32_t)ncl;
     for (int k4 = 0; k4 < sc.clist_words - 1; ++k4) {
@@ -864,7 +866,7 @@ struct Sim {
     int limitState = (int)(jru(h + J_PK) & 3u);
     if (!jd.enableMotor || fixedRotation) motorImpulse = 0.0f;
     if (jd.enableLimit && !fixedRotation) {
-      float jointAngle = aB - aA - 0.0f;  // referenceAngle = 0 (world_env.py:255-266)
+      float jointAngle = aB - aA - jr[h + J_REF];
       if (absb(jd.upper - jd.lower) < 2.0f * kAngularSlop) limitState = 3;
       else if (jointAngle <= jd.lower) { if (limitState != 1) impz = 0.0f; limitState = 1; }
       else if (jointAngle >= jd.upper) { if (limitState != 2) impz = 0.0f; limitState = 2; }
@@ -1056,7 +1058,7 @@ struct Sim {
       // angular limit, branch-free: the three active cases of b2RevoluteJoint::SolvePositionConstraints differ only in
       // the reference angle, the slop shift and the clamp interval; an inactive limit applies a zero impulse
       const bool limited = jd.enableLimit && limitState != 0 && !fixedRotation;
-      float angle = aB - aA - 0.0f;
+      float angle = aB - aA - jr[h + J_REF];
       float motorMass = jr[h + J_MM];
       float C0 = angle - (limitState == 2 ? jd.upper : jd.lower);
       float shift = limitState == 1 ? kAngularSlop : (limitState == 2 ? -kAngularSlop : 0.0f);
@@ -1587,6 +1589,9 @@ struct Sim {
       int h = kHotJoint * j;
       jr[h + J_IX] = 0.0f; jr[h + J_IY] = 0.0f; jr[h + J_IZ] = 0.0f; jr[h + J_MI] = 0.0f; jr[h + J_MS] = 0.0f;
       jru(h + J_PK) = 0u;
+      // pybox2d's revoluteJointDef(bodyA=, bodyB=, ...) sets referenceAngle = bodyB.angle - bodyA.angle when the joint is
+      // defined (world_env.py:255-266): limits are relative to the pose the robot is assembled in (oracle/b2_oracle.cpp)
+      jr[h + J_REF] = pose[sc.joint[j].b][2] - pose[sc.joint[j].a][2];
     }
   }
 

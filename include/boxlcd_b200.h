@@ -52,7 +52,8 @@ extern "C" {
 enum { BLCD_SHAPE_CIRCLE = 0, BLCD_SHAPE_BOX = 1, BLCD_SHAPE_POLYGON = 2 };
 enum { BLCD_ROLE_OBJECT = 0, BLCD_ROLE_ROOT = 1, BLCD_ROLE_CHILD = 2 };
 enum { BLCD_RASTER_PIL12 = 0, BLCD_RASTER_PIL9 = 1 };
-/* spec.flags: Box2D revision switches (default 0 = the 2.3.1+ forms) and ablation switches */
+/* spec.flags: Box2D revision switches (0 = the 2.3.1+ forms; the host layer's default is BLCD_FLAG_DAMPING_2_3_0, which is
+ * what pybox2d 2.3.10's recorded episodes show) and ablation switches */
 enum {
   BLCD_FLAG_DAMPING_2_3_0 = 1,   /* v *= clamp(1 - h*d, 0, 1) instead of the Pade form 1/(1+h*d) */
   BLCD_FLAG_REFFACE_2_3_0 = 2,   /* b2CollidePolygons as in 2.3.0: hill-climbing b2FindMaxSeparation, reference-face rule

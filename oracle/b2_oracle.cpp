@@ -127,7 +127,11 @@ void build_world(Env& env, const blcd_spec& sp, const float (*pose)[3]) {
       j.bodyB = sp.n_walls + jd.body_b;
       j.localAnchorA = Vec2(f32(jd.anchor_a[0]), f32(jd.anchor_a[1]));
       j.localAnchorB = Vec2(f32(jd.anchor_b[0]), f32(jd.anchor_b[1]));
-      j.referenceAngle = 0.0f;
+      // pybox2d's revoluteJointDef(bodyA=, bodyB=, localAnchorA=, ...) (world_env.py:255-266) fills referenceAngle with
+      // bodyB.angle - bodyA.angle at definition time: the limits [lower, upper] are relative to the pose the robot is
+      // assembled in.  Pinned by the recorded robot episodes (tests/test_gif_episodes.py); with referenceAngle = 0 the
+      // legs of the urchin snap into a 2-rad fan within a few frames, which the recordings do not show.
+      j.referenceAngle = pose[jd.body_b][2] - pose[jd.body_a][2];
       j.enableLimit = jd.enable_limit != 0;
       j.enableMotor = jd.enable_motor != 0;
       j.lowerAngle = f32(jd.lower);

@@ -1,0 +1,71 @@
+"""Pin the joint / motor / limit physics against REAL pybox2d output: the robot episodes the reference author recorded
+into /root/reference/assets/envs/{Urchin,Luxo,UrchinBall,UrchinCube,LuxoBall}.gif.
+
+The recorder is research/scripts/evaluations/demo_imgs.py:59-72: `env.seed(7)`, `np_random = RandomState(4)`,
+`env.reset()`, then per step `action = np_random.uniform(-1, 1, A)`, `env.step(action)`, one frame.  With gym==0.17.3
+(requirements.txt:2) `env.seed(7)` seeds a RandomState from sha512("7") (gym/utils/seeding.py: hash_seed ->
+_int_list_from_bigint), so the whole episode is a deterministic function of the reference's reset code.  This script
+  1. runs the UNMODIFIED reference `WorldEnv.reset()` under the recording stubs of ref_harness.py with that seeding and
+     stores the initial poses of every body,
+  2. stores the action sequence and the LCD panel of every gif frame (frame f shows the state after f + 1 steps),
+in tests/golden/gif_episodes.npz (keys `<Env>_init` [B, 3], `<Env>_actions` [T, A], `<Env>_lcd`, `<Env>_shape`).
+tests/test_gif_episodes.py replays them through the oracle (and the CUDA path on a GPU).
+
+Run in the build container only (needs /root/reference and PIL):   python tests/golden/make_robot_gif_episodes.py
+"""
+import hashlib
+import os
+import struct
+import sys
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import ref_harness  # noqa: E402
+from fit_gif_episodes import gif_lcd  # noqa: E402
+
+ENV_SEED, ACTION_SEED = 7, 4     # demo_imgs.py:60-61
+ROBOT_GIFS = ['Urchin', 'Luxo', 'UrchinBall', 'UrchinCube', 'LuxoBall']
+# LuxoCube.gif does not start from this seed's reset (frame 0 is already one pixel column off): recorded differently.
+
+
+def gym_0_17_random_state(seed):
+  """gym 0.17.3 seeding.np_random(seed): RandomState seeded with the 32-bit words of sha512(str(seed))[:8]"""
+  h = hashlib.sha512(str(seed).encode('utf8')).digest()[:8]
+  h += b'\0' * (4 - len(h) % 4)
+  words = struct.unpack('{}I'.format(len(h) // 4), h)
+  big = sum(2 ** (32 * i) * v for i, v in enumerate(words))
+  ints = []
+  while big > 0:
+    big, mod = divmod(big, 2 ** 32)
+    ints.append(mod)
+  rs = np.random.RandomState()
+  rs.seed(ints or [0])
+  return rs
+
+
+def main():
+  boxLCD = ref_harness.ref_envs()
+  import gym.utils.seeding as seeding
+  seeding.np_random = lambda seed=None: (gym_0_17_random_state(seed), seed)
+  path = os.path.join(HERE, 'gif_episodes.npz')
+  out = dict(np.load(path)) if os.path.exists(path) else {}
+  for name in ROBOT_GIFS:
+    env = boxLCD.env_map[name]()
+    env.seed(ENV_SEED)
+    env.reset()
+    init = np.array([[b.position[0], b.position[1], b.angle] for b in env.dynbodies.values()], np.float32)
+    lcd = gif_lcd(f'/root/reference/assets/envs/{name}.gif')
+    rs = np.random.RandomState(ACTION_SEED)
+    actions = np.array([rs.uniform(-1, 1, env.action_space.shape[0]) for _ in range(lcd.shape[0])])
+    out[f'{name}_init'] = init
+    out[f'{name}_actions'] = actions            # float64, as the recorder passed them to env.step
+    out[f'{name}_lcd'] = np.packbits(lcd, axis=2)
+    out[f'{name}_shape'] = np.array(lcd.shape)
+    print(name, 'bodies', init.shape, 'actions', actions.shape, 'frames', lcd.shape)
+  np.savez_compressed(path, **out)
+
+
+if __name__ == '__main__':
+  main()

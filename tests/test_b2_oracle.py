@@ -106,22 +106,34 @@ def test_ball_ball_collision_conserves_momentum_without_gravity():
   assert out[1, 3] - out[0, 3] == pytest.approx(0.8 * 3.0, rel=2e-2)
 
 
-def test_urchin_legs_are_driven_inside_their_limits():
+def test_urchin_legs_stay_within_their_limits_around_the_assembly_pose():
+  """limits [-1, 1] are relative to the angle each leg is assembled at (0, 2.0, 4.2 rad from the root): pybox2d fills
+  referenceAngle = bodyB.angle - bodyA.angle when the joint is defined (pinned by the recorded Urchin episode)"""
   env, ow = worlds('Urchin', n=16)
   ow.reset()
-  for _ in range(30):
-    ow.step(np.zeros((16, 3), np.float32))
-  b = ow.get_bodies()
+  rng = np.random.RandomState(0)
   slop = 2.0 / 180 * math.pi
-  for leg in (1, 2, 3):
-    rel = b[:, leg, 2] - b[:, 0, 2]
-    rel = rel - 2 * math.pi * np.round(rel / (2 * math.pi))   # body angles are unwrapped; limits apply to the raw difference mod 2pi here
-    assert (np.abs(rel) <= 1.0 + slop + 0.05).all(), rel
-  # revolute anchors stay pinned: leg anchor (0, 20/30) in leg frame == root origin
+  devs = []
+  for t in range(40):
+    ow.step(np.sign(rng.uniform(-1, 1, (16, 3))).astype(np.float32))   # full speed either way
+    b = ow.get_bodies()
+    for leg, rest in zip((1, 2, 3), (0.0, 2.0, 4.2)):
+      rel = b[:, leg, 2] - b[:, 0, 2] - rest
+      devs.append(np.abs(rel - 2 * math.pi * np.round(rel / (2 * math.pi))))
+  devs = np.array(devs)
+  # Box2D's limits are soft (a leg jammed against the floor can be held past its stop), but nothing like the 2 rad a
+  # zero reference angle would make of the legs assembled at 2.0 and 4.2 rad
+  assert (devs <= 1.0 + slop + 0.1).mean() > 0.85 and (devs <= 1.0 + slop + 0.3).mean() > 0.97 and devs.max() < 1.7
+  assert devs.max() > 0.9     # and the motors do drive the legs to their stops
+  # revolute anchors stay pinned: leg anchor (0, 20/30) in leg frame == root origin (to a few centimetres: continuous
+  # collision moves bodies without regard for joints, and full-speed motors against the floor keep re-opening the hinge)
+  gaps = []
   for leg in (1, 2, 3):
     ax = b[:, leg, 0] - np.sin(b[:, leg, 2]) * (20 / 30)
     ay = b[:, leg, 1] + np.cos(b[:, leg, 2]) * (20 / 30)
-    assert np.abs(ax - b[:, 0, 0]).max() < 0.02 and np.abs(ay - b[:, 0, 1]).max() < 0.02
+    gaps.append(np.hypot(ax - b[:, 0, 0], ay - b[:, 0, 1]))
+  gaps = np.array(gaps)
+  assert (gaps < 0.02).mean() > 0.9 and gaps.max() < 0.25
 
 
 def test_motor_reaches_commanded_speed_in_free_space():
