@@ -107,7 +107,7 @@ BLCD_HD RowMask polygon_row(const PolyPx& P, int y, int w, int h, int rules, int
     int j = i + 1 < n ? i + 1 : 0;
     int ex0 = P.x[i], ey0 = P.y[i], ex1 = P.x[j], ey1 = P.y[j];
     if (ey0 == ey1) {
-      if (ey0 == y) mask |= span_mask(ex0, ex1, w);
+      if (ey0 == y && rules != BLCD_RASTER_PIL9) mask |= span_mask(ex0, ex1, w);   // the older Pillow skips horizontal edges
       continue;
     }
     if (!in_range) continue;

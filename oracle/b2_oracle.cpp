@@ -9,9 +9,11 @@
  * The Box2D arithmetic lives in b2_world.h / b2_collide.h / b2_math.h (restated from upstream Box2D 2.3.x, the
  * third-party C++ behind pybox2d `Box2D==2.3.10`, requirements.txt:17; sources not under /root/reference).
  *
- * PARITY UNPINNED for the physics: neither pybox2d nor Box2D sources exist in this image, and the reference ships no
- * tests or golden vectors for this path.  What IS pinned: the LCD renderer (lcd_oracle.c vs the unmodified reference
- * renderer) and the reset distribution / observation layout (vs the reference run under stubs, tests/golden/).
+ * Neither pybox2d nor Box2D sources exist in this image and the reference ships no tests for this path; the physics is
+ * PINNED against the episodes the reference author recorded with real pybox2d (assets/envs/*.gif): passive scenes frame
+ * for frame, robot scenes (joints, motors, limits) for 9-12 s of random actions each (tests/test_gif_episodes.py,
+ * oracle/README.md).  Also pinned: the LCD renderer (lcd_oracle.c vs the unmodified reference renderer) and the reset
+ * distribution / observation layout (vs the reference run under stubs, tests/golden/).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may call into this library.
  */

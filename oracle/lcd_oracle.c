@@ -11,8 +11,9 @@
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may call into this file.
  *
- * Rule sets: 0 = "pil12" (pinned here), 1 = "pil9" (the reference's own pin; cannot be checked in this image:
- * no apex extension, no inverted-span skip).
+ * Rule sets: 0 = "pil12" (pinned here against this image's Pillow), 1 = "pil9" (the Pillow of the reference's recorded
+ * episodes: no apex extension, no span-overlap bookkeeping, horizontal edges not drawn; checked against the recorded robot
+ * gifs, tests/test_gif_episodes.py -- 95 % of their frames bit-exact, not pinned pixel for pixel).
  */
 #include <math.h>
 #include <stdint.h>
@@ -121,7 +122,9 @@ static void fill_polygon(canvas* cv, const int (*P)[2], int n, int rules) {
     if (e->ymin < ylo) ylo = e->ymin;
     if (e->ymax > yhi) yhi = e->ymax;
     if (e->y0 == e->y1) {
-      hline(cv, e->x0, e->y0, e->x1);
+      /* current Pillow draws horizontal edges as spans of their own; the Pillow behind the reference's recorded episodes
+       * (requirements.txt pins 9.0.1) did not: a limb lying flat inside one pixel row is invisible there */
+      if (rules != 1) hline(cv, e->x0, e->y0, e->x1);
       continue;
     }
     e->dx = (float)(e->x1 - e->x0) / (float)(e->y1 - e->y0);

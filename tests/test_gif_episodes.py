@@ -121,11 +121,14 @@ def test_cubes_episode_under_both_box2d_rule_sets():
 # The recorder (research/scripts/evaluations/demo_imgs.py:59-72) seeds the env with 7 and draws actions from
 # RandomState(4), so these episodes need no fitting: tests/golden/make_robot_gif_episodes.py runs the unmodified
 # reference reset() with gym 0.17.3's seeding for the initial poses and stores the action sequence.  Frames were rendered
-# by Pillow 9.0.1 (requirements.txt), whose thin-polygon fill differs from today's Pillow in a few pixels: the replay uses
-# the 'pil9' rule set (a restatement from the published 9.0 source, not pinned pixel for pixel), and a frame counts as
-# reproduced when it is bit-exact; the other frames must stay within a handful of pixels.
+# by the author's Pillow (requirements.txt pins 9.0.1), whose polygon fill differs from today's in a few pixels of thin
+# limbs: the replay uses the 'pil9' rule set (no overlap bookkeeping between spans, no apex extension, horizontal edges not
+# drawn -- the variant that explains most recorded frames out of 64 tried, tools/raster_rule_search.py).  A frame counts as
+# reproduced when it is bit-exact; the others must stay within a handful of pixels.  UrchinCube is bit-exact for its first
+# 125 frames (12.5 s); where episodes leave the recording they do so late and gradually, as last-bit libm differences
+# (sinf / cosf of the author's glibc) are amplified by the contact dynamics.
 #   name: (frames that must track the recording, min bit-exact among them, max pixel difference among them)
-ROBOT_GIFS = {'Urchin': (100, 85, 8), 'Luxo': (100, 85, 8), 'UrchinCube': (125, 118, 5), 'UrchinBall': (90, 80, 6), 'LuxoBall': (88, 74, 6)}
+ROBOT_GIFS = {'Urchin': (100, 87, 4), 'Luxo': (100, 92, 6), 'UrchinCube': (125, 125, 0), 'UrchinBall': (90, 82, 6), 'LuxoBall': (88, 76, 6)}
 
 
 def load_robot(name):
