@@ -10,7 +10,7 @@
  * third-party C++ behind pybox2d `Box2D==2.3.10`, requirements.txt:17; sources not under /root/reference).
  *
  * Neither pybox2d nor Box2D sources exist in this image and the reference ships no tests for this path; the physics is
- * PINNED against the episodes the reference author recorded with real pybox2d (assets/envs/*.gif): passive scenes frame
+ * PINNED against the episodes the reference author recorded with real pybox2d (the gifs under assets/envs/): passive scenes frame
  * for frame, robot scenes (joints, motors, limits) for 9-12 s of random actions each (tests/test_gif_episodes.py,
  * oracle/README.md).  Also pinned: the LCD renderer (lcd_oracle.c vs the unmodified reference renderer) and the reset
  * distribution / observation layout (vs the reference run under stubs, tests/golden/).
