@@ -1,7 +1,9 @@
 """Physics pinned against REAL pybox2d output: the episodes recorded in the reference's own assets
-(`assets/envs/*.gif`, LCD half of every frame, extracted by tests/golden/fit_gif_episodes.py).  For each passive env a
-stored initial state (bodies at rest) must reproduce EVERY frame of the reference's episode bit-exactly when stepped with
-this repo's simulators: that exercises gravity integration, the 3 x (1/30 s) sub-stepping, circle / polygon / edge narrow
+(`assets/envs/*.gif`, LCD half of every frame).  The recorder seeds the env (demo_imgs.py:60), so for Bounce, Dropbox,
+Bounce2 and Object2 the initial state is simply what the unmodified reference reset() samples under that seed
+(tests/golden/make_robot_gif_episodes.py) -- nothing is fitted; Object2-circles / Object2-cubes were recorded with forced
+shapes and use an initial state fitted to the recording (tests/golden/fit_gif_episodes.py).  Each initial state must
+reproduce EVERY frame of the reference's episode bit-exactly when stepped with this repo's simulators: that exercises gravity integration, the 3 x (1/30 s) sub-stepping, circle / polygon / edge narrow
 phase, restitution, friction, the 2-point block solver, continuous collision (without TOI the first bounce already
 differs) and the LCD rasterizer, against what Box2D 2.3.10 + Pillow produced for the author."""
 import os
