@@ -4,8 +4,13 @@ import collections, csv, os, re, subprocess, sys, tempfile
 rep, so, kname = sys.argv[1], sys.argv[2], sys.argv[3]
 tmp = tempfile.mkdtemp()
 subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(so)], cwd=tmp, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.endswith('.cubin')][0]
-dis = subprocess.run(['nvdisasm', '--print-line-info', '-c', os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split('\n')
+# the library holds one cubin per scene-size profile; take the one whose kernel matches (kname may include the profile namespace)
+dis = []
+for cubin in sorted(f for f in os.listdir(tmp) if f.endswith('.cubin')):
+  d = subprocess.run(['nvdisasm', '--print-line-info', '-c', os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split('\n')
+  if any(l.startswith('.text.') and all(k in l for k in kname.split('+')) for l in d):
+    dis = d
+    break
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.split('\n')))
 hdr, vals = rows[0], rows[2]
@@ -19,7 +24,7 @@ for k in ['gpu__time_duration.sum', 'smsp__inst_executed.sum', 'smsp__thread_ins
   if k in hdr: print(f'{k:90s} {get(k)}')
 srcrows = list(csv.reader(subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout.split('\n')))
 kfull = srcrows[0][1]
-start = [i for i, l in enumerate(dis) if l.startswith('.text.') and kname in l][0]
+start = [i for i, l in enumerate(dis) if l.startswith('.text.') and all(k in l for k in kname.split('+'))][0]
 off2loc, cur = {}, ('?', 0)
 for l in dis[start + 1:]:
   if l.startswith('//--------------------- .'): break
