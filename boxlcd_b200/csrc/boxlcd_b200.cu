@@ -371,7 +371,7 @@ struct BLCD_PENV {
   cudaStream_t hstream[kHostStreams] = {};              // blcd_step_host's pipeline streams
   cudaEvent_t hev[kHostDepth][kHostStreams] = {};       // completion of host step s (ring) on each stream
   uint64_t host_submitted = 0, host_completed = 0;
-  int host_chunks = 0;
+  int host_chunks = 0, host_chunks_env = -1;
 };
 
 namespace {
@@ -712,10 +712,13 @@ static int host_step_buffers(BLCD_PENV* h, size_t* na, size_t* nf, size_t* nb, s
   return 0;
 }
 
-static int host_chunks_default(const BLCD_PENV* h) {
-  int chunks = h->timing ? 1 : kHostStreams;
-  if (const char* e = getenv("BLCD_HOST_CHUNKS")) chunks = atoi(e);
-  return chunks;
+static int host_chunks_default(BLCD_PENV* h) {
+  if (h->host_chunks_env < 0) {   // read the override once per handle
+    const char* e = getenv("BLCD_HOST_CHUNKS");
+    h->host_chunks_env = e ? atoi(e) : 0;
+  }
+  if (h->host_chunks_env > 0) return h->host_chunks_env;
+  return h->timing ? 1 : kHostStreams;
 }
 
 int BLCD_P(step_host)(BLCD_PENV* h, const float* actions_host, float* full_state_host, uint32_t* lcd_bits_host, uint8_t* done_host) {

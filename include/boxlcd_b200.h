@@ -156,7 +156,11 @@ int blcd_step_observe(blcd_handle h, const float* actions_dev, float* actions_ou
 int blcd_rollout(blcd_handle h, int32_t T, float* full_state_dev, uint32_t* lcd_bits_dev, float* actions_dev, uint64_t stream);
 
 /* Host-buffer variant of step + observe (the call an unmodified reference-side caller would bind): copies actions
- * host->device, steps, observes, copies full_state and packed frames device->host, and synchronizes. */
+ * host->device, steps, observes, copies full_state and packed frames device->host, and synchronizes.
+ * The caller's buffers are page-locked in place on first use (cudaHostRegister; the eight most recent buffers stay
+ * registered until blcd_destroy) so that the copies are direct DMA transfers; if the driver refuses, the call stages
+ * through pinned memory of its own.  Keep a buffer alive until the handle is destroyed or eight other buffers have been
+ * used since. */
 int blcd_step_host(blcd_handle h, const float* actions_host, float* full_state_host, uint32_t* lcd_bits_host, uint8_t* done_host);
 
 /* The same split into submit and wait, the call shape of the reference's AsyncVectorEnv.step_async / step_wait
