@@ -200,6 +200,7 @@ def main():
     one_step()
     kern_ms.append(None)
   e1.record()
+  launches = v.kernel_launches - launches0     # kernels of this library launched inside the timed region: (k_reset + k_rollout) per step
   barrier()
   # the rollout kernel's own duration (CUDA events recorded by the library around the launch, on the launching stream)
   v.enable_timing(True)
@@ -210,7 +211,6 @@ def main():
     torch.cuda.synchronize()
     one_kernel.append(v.last_step_ms())
   clocks = sampler.stop() if rank == 0 else None
-  launches = v.kernel_launches - launches0
   total_ms = e0.elapsed_time(e1)
   t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
   if world_size > 1:
