@@ -193,18 +193,9 @@ class VecWorldEnv:
             'lcd': self.unpack_lcd(obs['lcd_bits']).cpu().numpy()}
 
   def reset(self, idxs=None, full_state=None, proprio=None):
-    if proprio is not None:
-      proprio = np.asarray(proprio, np.float32)
-      full_state = np.zeros(proprio.shape[:-1] + (self.S,), np.float32)
-      full_state[..., self.env.pobs_idxs] = proprio
-    idx_t = None if idxs is None else torch.as_tensor(np.asarray(idxs, np.int64)).to(self.device)
-    fs_t = None if full_state is None else torch.as_tensor(np.ascontiguousarray(full_state, np.float32)).to(self.device)
-    self.reset_dev(idx_t, fs_t)
-    obs = self._obs_numpy(self.observe_dev())
-    if idxs is not None:
-      sel = np.asarray(idxs, np.int64)
-      obs = {k: v[sel] for k, v in obs.items()}
-    return obs
+    """AsyncVectorEnv.reset(idxs, **kwargs): reset the listed worlds (None = all), optionally from states / proprio vectors"""
+    self.reset_async(idxs, full_state=full_state, proprio=proprio)
+    return self.reset_wait(idxs)
 
   def observe(self):
     return self._obs_numpy(self.observe_dev())
@@ -214,6 +205,44 @@ class VecWorldEnv:
     obs, _ = self.step_dev(a, observe=True)
     done = obs['done'].cpu().numpy().astype(bool)
     return self._obs_numpy(obs), np.zeros(self.n), done, [{'timeout': bool(d)} for d in done]
+
+  # -- AsyncVectorEnv's split calls (research/wrappers/async_vector_env.py:131-242) ---------------------------------------
+  # *_async enqueues the kernel on the current CUDA stream and returns at once; *_wait copies the result to the host.
+  def step_async(self, actions):
+    if getattr(self, '_pending', None) is not None:
+      raise RuntimeError(f'Calling `step_async` while waiting for a pending call to `{self._pending[0]}` to complete.')
+    a = torch.as_tensor(np.ascontiguousarray(actions, np.float32).reshape(self.n, self.A)).to(self.device, non_blocking=True)
+    obs, _ = self.step_dev(a, observe=True)
+    self._pending = ('step', obs)
+
+  def step_wait(self, timeout=None):
+    if getattr(self, '_pending', None) is None or self._pending[0] != 'step':
+      raise RuntimeError('Calling `step_wait` without any prior call to `step_async`.')
+    obs, self._pending = self._pending[1], None
+    done = obs['done'].cpu().numpy().astype(bool)
+    return self._obs_numpy(obs), np.zeros(self.n), done, [{'timeout': bool(d)} for d in done]
+
+  def reset_async(self, idxs=None, **kwargs):
+    if getattr(self, '_pending', None) is not None:
+      raise RuntimeError(f'Calling `reset_async` while waiting for a pending call to `{self._pending[0]}` to complete.')
+    full_state, proprio = kwargs.get('full_state'), kwargs.get('proprio')
+    if proprio is not None:
+      proprio = np.asarray(proprio, np.float32)
+      full_state = np.zeros(proprio.shape[:-1] + (self.S,), np.float32)
+      full_state[..., self.env.pobs_idxs] = proprio
+    idx_t = None if idxs is None else torch.as_tensor(np.asarray(idxs, np.int64)).to(self.device)
+    fs_t = None if full_state is None else torch.as_tensor(np.ascontiguousarray(full_state, np.float32)).to(self.device)
+    self.reset_dev(idx_t, fs_t)
+    self._pending = ('reset', self.observe_dev())
+
+  def reset_wait(self, idxs=None, timeout=None):
+    if getattr(self, '_pending', None) is None or self._pending[0] != 'reset':
+      raise RuntimeError('Calling `reset_wait` without any prior call to `reset_async`.')
+    obs, self._pending = self._obs_numpy(self._pending[1]), None
+    if idxs is not None:
+      sel = np.asarray(idxs, np.int64)
+      obs = {k: v[sel] for k, v in obs.items()}
+    return obs
 
   def render(self, width=None, height=None):
     """lcd_render(width, height) for every world from its current pose -> bool [N, height, width]"""

@@ -165,6 +165,18 @@ def test_step_observe_and_vector_env_call_shape():
   for t in range(3):
     _, _, done, infos = v2.step(np.zeros((4, 1), np.float32))
   assert done.all() and infos[0]['timeout']
+  # the split calls of AsyncVectorEnv (async_vector_env.py:131-242) give the same results and the same misuse errors
+  va, vb = vec(env, n, seed=3), vec(env, n, seed=3)
+  va.reset_async(); oa = va.reset_wait()
+  ob = vb.reset()
+  assert all((oa[k] == ob[k]).all() for k in oa)
+  va.step_async(a)
+  with pytest.raises(RuntimeError, match='pending call to `step`'):
+    va.step_async(a)
+  ra, rb = va.step_wait(), vb.step(a)
+  assert all((ra[0][k] == rb[0][k]).all() for k in ra[0]) and (ra[2] == rb[2]).all()
+  with pytest.raises(RuntimeError, match='without any prior call'):
+    va.step_wait()
 
 
 def test_single_env_api_is_a_drop_in():
