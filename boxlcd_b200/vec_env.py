@@ -254,3 +254,15 @@ class VecWorldEnv:
     poses, variants = self.get_poses_dev()
     bits = self.render_poses_dev(poses, variants, width, height)
     return self.unpack_lcd(bits, width).cpu().numpy()
+
+
+class AsyncVectorEnv(VecWorldEnv):
+  """Constructor shape of the reference's `research/wrappers/async_vector_env.AsyncVectorEnv(env_fns, ...)`: callers such as
+  `research/data.py:24-29` build `AsyncVectorEnv([env_fn(G) for _ in range(G.num_envs)])`; here the list only tells how many
+  worlds to allocate -- one instance is built for the scene description, and all worlds live in one GPU batch (the
+  multiprocessing options are accepted and ignored)."""
+
+  def __init__(self, env_fns, observation_space=None, action_space=None, shared_memory=True, copy=True, context=None, daemon=True, worker=None,
+               device=None, seed=0):
+    env_fns = list(env_fns)
+    super().__init__(env_fns[0](), len(env_fns), device=device, seed=seed)

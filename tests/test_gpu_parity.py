@@ -208,3 +208,26 @@ def test_state_save_load_round_trip_and_sharding_invariance():
   full = vec(env, 512, seed=9); full.reset_dev(); f = full.rollout_dev(8)['full_state']
   half = vec(env, 256, seed=9, world_offset=256); half.reset_dev(); h = half.rollout_dev(8)['full_state']
   assert torch.equal(f[256:], h)
+
+
+def test_reference_collector_loop_runs_on_the_vector_env():
+  """research/data.py:24-61 with only the import changed: AsyncVectorEnv([env_fn] * N), reset(np.arange(N)), action_space.sample(),
+  np.stack(act), step(act)"""
+  from boxlcd_b200.vec_env import AsyncVectorEnv
+  num_envs, ep_len = 20, 7
+  env_fn = lambda: blcd.envs.LuxoCube({'ep_len': ep_len})
+  env = env_fn()
+  venv = AsyncVectorEnv([env_fn for _ in range(num_envs)])
+  obses = {key: np.zeros([num_envs, ep_len, *val.shape], dtype=val.dtype) for key, val in env.observation_space.spaces.items()}
+  acts = np.zeros([num_envs, ep_len, env.action_space.shape[0]])
+  obs = venv.reset(np.arange(num_envs))
+  for j in range(ep_len):
+    act = venv.action_space.sample()
+    for key in obses:
+      obses[key][:, j] = obs[key]
+    acts[:, j] = np.stack(act)
+    obs, rew, done, info = venv.step(act)
+  assert done.all() and obses['proprio'].ndim == 3 and acts.ndim == 3
+  assert obses['lcd'].dtype == bool and obses['lcd'].shape == (num_envs, ep_len, 16, 24)
+  assert np.abs(acts).max() <= 1.0 and np.isfinite(obses['full_state']).all() and (obses['lcd'] == 0).any()
+  venv.close()
