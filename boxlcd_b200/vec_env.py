@@ -27,9 +27,9 @@ class VecWorldEnv:
     if self.device.index is None:
       self.device = torch.device('cuda', torch.cuda.current_device())
     self.l = _lib.lib()
-    h = C.c_void_p()
-    _lib.check(self.l.blcd_create(C.byref(self.spec), self.n, self.device.index, int(seed or 0), int(world_offset), C.byref(h)))
-    self.h = h
+    self.world_offset = int(world_offset)
+    self.h = None
+    self._create(seed)
     sp = self.spec
     self.B, self.S, self.A, self.P = sp.n_bodies, sp.obs_size, sp.act_size, max(sp.pobs_size, 1)
     self.H, self.W = sp.lcd_h, sp.lcd_w
@@ -42,6 +42,20 @@ class VecWorldEnv:
     self._bits = torch.empty((self.n,) + self.bits_shape(), dtype=torch.int32, device=self.device)
     self._done = torch.empty((self.n,), dtype=torch.uint8, device=self.device)
     self._act = torch.empty((self.n, self.A), **f32)
+
+  def _create(self, seed):
+    h = C.c_void_p()
+    _lib.check(self.l.blcd_create(C.byref(self.spec), self.n, self.device.index, int(seed or 0), self.world_offset, C.byref(h)))
+    self.h, self._seed = h, int(seed or 0)
+
+  def seed(self, seeds=None):
+    """AsyncVectorEnv.seed (async_vector_env.py:108-129): re-key the per-world random streams.  Worlds draw from Philox streams
+    keyed by (seed, global world index), so one integer seeds them all; a list is reduced to its first entry.  The
+    simulation state is rebuilt: call reset() afterwards, as with the reference (seeding only affects later resets)."""
+    if seeds is not None and not isinstance(seeds, (int, np.integer)):
+      seeds = list(seeds)[0]
+    self.close()
+    self._create(0 if seeds is None else int(seeds))
 
   # -- lifetime -------------------------------------------------------------------------------------------------------
   def close(self):

@@ -270,3 +270,14 @@ def test_async_host_steps_match_synchronous_steps():
     assert (fs[t] == fs2).all() and (bits[t] == bits2).all() and (dn[t] == dn2).all(), t
   # device-side calls issued afterwards see the state after all T steps
   assert (v.observe()['full_state'] == fs[-1]).all()
+
+
+def test_vector_env_seed_rekeys_the_world_streams():
+  env = make_env('Urchin')
+  v = vec(env, 64, seed=1)
+  a = v.reset()['full_state']
+  v.seed(2)
+  b = v.reset()['full_state']
+  v.seed([1] * 64)
+  c = v.reset()['full_state']
+  assert (a == c).all() and (a != b).any()
