@@ -384,7 +384,9 @@ int launch_sized(BLCD_PENV* h, F f) {
     case 64: return f(std::integral_constant<int, 64>());
     case 128: return f(std::integral_constant<int, 128>());
     case 256: return f(std::integral_constant<int, 256>());
+    case 320: return f(std::integral_constant<int, 320>());
     case 384: return f(std::integral_constant<int, 384>());
+    case 448: return f(std::integral_constant<int, 448>());
     case 512: return f(std::integral_constant<int, 512>());
     default: return fail("unsupported block size");
   }
@@ -426,15 +428,39 @@ int BLCD_P(create)(const blcd_spec* spec_host, int64_t n_worlds, int device, uin
   if (err) { delete h; return fail(std::string("blcd_create: ") + err); }
   if (const char* e = getenv("BLCD_ALIGN")) h->scene.align_mode = atoi(e);
   h->n = n_worlds; h->device = device; h->seed = seed; h->world_offset = world_offset;
-  // block size: largest of 128/64/32 that still lets several blocks share an SM's shared memory
   int smem_max = 0;
   CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  // one 256-thread block per SM: the register file (<= 255 registers x 256 threads) is the occupancy limit, and all eight
-  // warps of the block walk the solver phases together (Sim::phase_align)
+  // One block per SM (the register file is the occupancy limit) whose warps walk the solver phases together
+  // (Sim::phase_align).  A launch therefore takes waves x (time of one block), waves = ceil(blocks / SMs).
+  //  * articulated scenes: 256 threads.  Below 253 registers per thread the joint records spill, and a block's time grows
+  //    almost as fast as its size (Urchin, relative to 256 threads: 320 1.21, 384 1.37, 448 1.74, 512 1.82; LuxoCube loses
+  //    8 % at 384), so fewer, larger waves do not pay.
+  //  * joint-free scenes (balls, boxes): a block's time grows slowly with its size (Bounce2: 448 threads 1.26), so the size
+  //    with the smallest waves x time estimate for this world count wins -- 65 536 Bounce2 worlds fit ONE wave of
+  //    448-thread blocks instead of two of 256 (+33 %), 262 144 take 4 waves instead of 7 (+17 %).
+  int sm_count = 148;
+  CK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
   h->block = 256;
+  if (h->scene.nj == 0) {
+    const int sizes[] = {256, 320, 384, 448, 512};
+    const double rel[] = {1.00, 1.09, 1.175, 1.26, 1.35};
+    double best = 0.0;
+    for (int i = 0; i < 5; ++i) {
+      if (smem_bytes(h, sizes[i]) > (size_t)smem_max) continue;
+      const int64_t blocks = (n_worlds + sizes[i] - 1) / sizes[i], waves = (blocks + sm_count - 1) / sm_count;
+      const double cost = (double)waves * rel[i];
+      if (best == 0.0 || cost < best * 0.995) { best = cost; h->block = sizes[i]; }   // near-ties keep the smaller block
+    }
+  }
   if (const char* e = getenv("BLCD_BLOCK")) h->block = atoi(e);
-  if (h->block != 64 && h->block != 128 && h->block != 256 && h->block != 384 && h->block != 512) h->block = 256;
-  while (h->block > 64 && smem_bytes(h, h->block) > (size_t)smem_max) h->block /= 2;
+  {
+    const int sizes[] = {512, 448, 384, 320, 256, 128, 64};
+    bool known = false;
+    for (int b : sizes) known |= (b == h->block);
+    if (!known) h->block = 256;
+    for (int b : sizes)   // the largest supported size not above the request whose working set fits shared memory
+      if (b <= h->block && smem_bytes(h, b) <= (size_t)smem_max) { h->block = b; break; }
+  }
   if (smem_bytes(h, h->block) > (size_t)smem_max) { delete h; return fail("scene working set does not fit shared memory"); }
   CK(cudaMalloc(&h->scene_dev, sizeof(DScene)));
   CK(cudaMemcpy(h->scene_dev, &h->scene, sizeof(DScene), cudaMemcpyHostToDevice));
