@@ -381,13 +381,14 @@ size_t smem_bytes(const BLCD_PENV* h, int block) { return (size_t)kSceneBytes + 
 template <typename F>
 int launch_sized(BLCD_PENV* h, F f) {
   switch (h->block) {
-    case 64: return f(std::integral_constant<int, 64>());
     case 128: return f(std::integral_constant<int, 128>());
     case 256: return f(std::integral_constant<int, 256>());
+#if BLCD_PROFILE_ID == 0   // the large profile is only ever launched with 256 threads (or 128 as the shared-memory fallback)
     case 320: return f(std::integral_constant<int, 320>());
     case 384: return f(std::integral_constant<int, 384>());
     case 448: return f(std::integral_constant<int, 448>());
     case 512: return f(std::integral_constant<int, 512>());
+#endif
     default: return fail("unsupported block size");
   }
 }
@@ -454,7 +455,11 @@ int BLCD_P(create)(const blcd_spec* spec_host, int64_t n_worlds, int device, uin
   }
   if (const char* e = getenv("BLCD_BLOCK")) h->block = atoi(e);
   {
-    const int sizes[] = {512, 448, 384, 320, 256, 128, 64};
+#if BLCD_PROFILE_ID == 0
+    const int sizes[] = {512, 448, 384, 320, 256, 128};
+#else
+    const int sizes[] = {256, 128};
+#endif
     bool known = false;
     for (int b : sizes) known |= (b == h->block);
     if (!known) h->block = 256;
