@@ -281,3 +281,25 @@ def test_vector_env_seed_rekeys_the_world_streams():
   v.seed([1] * 64)
   c = v.reset()['full_state']
   assert (a == c).all() and (a != b).any()
+
+
+@pytest.mark.parametrize('name', ['Bounce2', 'Object3', 'Urchin'])
+def test_results_do_not_depend_on_the_block_size(name, monkeypatch):
+  """blcd_create picks the block size from the scene and the world count; a world's arithmetic must not notice"""
+  env = make_env(name)
+  n, T = 3000, 25
+  outs = []
+  for block in ('128', '256', '320', '384', '448', '512'):
+    monkeypatch.setenv('BLCD_BLOCK', block)
+    v = vec(env, n, seed=9)
+    assert v.info()['block'] == int(block)
+    v.reset_dev()
+    r = v.rollout_dev(T)
+    obs, _ = v.step_dev(None)
+    outs.append([r[k].cpu().numpy() for k in ('full_state', 'lcd_bits', 'action')] + [obs['full_state'].cpu().numpy(), v.counters()])
+    v.close()
+  for o in outs[1:]:
+    for a, b in zip(outs[0], o):
+      assert (a == b).all()
+  monkeypatch.delenv('BLCD_BLOCK')
+  assert vec(make_env('Bounce2'), 65536).info()['block'] == 448 and vec(make_env('Urchin'), 65536).info()['block'] == 256
