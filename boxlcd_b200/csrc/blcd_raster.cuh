@@ -28,9 +28,11 @@ namespace BLCD_NS {
 // (int)(v / WIDTH * width) in fp64 (world_env.py:493-505: numpy float64 arithmetic, then PIL's C cast)
 BLCD_HD int to_px(double v, double world_w, double lcd_w) { return (int)(v / world_w * lcd_w); }
 
-// inclusive span [x0, x1] clipped to [0, w) as a bit mask; ends are swapped if inverted (Draw.c hline)
-BLCD_HD RowMask span_mask(int x0, int x1, int w) {
+// inclusive span [x0, x1] clipped to the window [x_off, x_off + w) as a bit mask (bit 0 = column x_off); ends are swapped if
+// inverted (Draw.c hline).  Frames wider than one RowMask are rendered as several such column windows.
+BLCD_HD RowMask span_mask(int x0, int x1, int w, int x_off = 0) {
   if (x0 > x1) { int t = x0; x0 = x1; x1 = t; }
+  x0 -= x_off; x1 -= x_off;
   if (x0 < 0) x0 = 0;
   if (x1 >= w) x1 = w - 1;
   if (x0 > x1) return 0u;
@@ -49,7 +51,7 @@ BLCD_HD long long ell_delta(long long a, long long b, long long x, long long y) 
 
 // ink of canvas row y for the filled ellipse inscribed in the integer box (x0, y0, x1, y1): Pillow's ellipseNew walk
 // of the first quadrant in doubled coordinates; the widest X reached at height |Y| gives the span of rows +-Y.
-BLCD_HD RowMask ellipse_row(int x0, int y0, int x1, int y1, int y, int w) {
+BLCD_HD RowMask ellipse_row(int x0, int y0, int x1, int y1, int y, int w, int x_off = 0) {
   int a = x1 - x0, b = y1 - y0;
   if (a < 0 || b < 0 || (a == 0 && b == 0)) return 0u;
   int sy = 2 * (y - y0) - b;
@@ -69,7 +71,7 @@ BLCD_HD RowMask ellipse_row(int x0, int y0, int x1, int y1, int y, int w) {
     }
     cx = nx; cy = ny;
   }
-  return span_mask(x0 + (a - cx) / 2, x0 + (a + cx) / 2, w);
+  return span_mask(x0 + (a - cx) / 2, x0 + (a + cx) / 2, w, x_off);
 }
 
 struct PolyPx {
@@ -82,7 +84,7 @@ BLCD_HD float edge_x_at(int ex0, int ey0, float dx, int y) { return BLCD_FADD(BL
 // ink of canvas row y for the filled polygon with integer vertices P (Pillow polygon_generic restated per row).
 // rules: BLCD_RASTER_PIL12 (pinned) or BLCD_RASTER_PIL9.
 // ylo_in / yhi_in: the polygon's vertex row range if the caller already has it (ylo_in > yhi_in: compute here)
-BLCD_HD RowMask polygon_row(const PolyPx& P, int y, int w, int h, int rules, int ylo_in = 1, int yhi_in = 0) {
+BLCD_HD RowMask polygon_row(const PolyPx& P, int y, int w, int h, int rules, int ylo_in = 1, int yhi_in = 0, int x_off = 0) {
   const int n = P.n;
   if (n <= 0) return 0u;
   // edge list: (P[i], P[i+1]) for i < n-1, plus the closing edge unless the last vertex repeats the first
@@ -107,7 +109,7 @@ BLCD_HD RowMask polygon_row(const PolyPx& P, int y, int w, int h, int rules, int
     int j = i + 1 < n ? i + 1 : 0;
     int ex0 = P.x[i], ey0 = P.y[i], ex1 = P.x[j], ey1 = P.y[j];
     if (ey0 == ey1) {
-      if (ey0 == y && rules != BLCD_RASTER_PIL9) mask |= span_mask(ex0, ex1, w);   // the older Pillow skips horizontal edges
+      if (ey0 == y && rules != BLCD_RASTER_PIL9) mask |= span_mask(ex0, ex1, w, x_off);   // the older Pillow skips horizontal edges
       continue;
     }
     if (!in_range) continue;
@@ -126,7 +128,7 @@ BLCD_HD RowMask polygon_row(const PolyPx& P, int y, int w, int h, int rules, int
   }
   if (!in_range) return mask;
   if (rules == BLCD_RASTER_PIL9) {
-    for (int k = 1; k < cnt; k += 2) mask |= span_mask(round_up_px(xx[k - 1]), round_down_px(xx[k]), w);
+    for (int k = 1; k < cnt; k += 2) mask |= span_mask(round_up_px(xx[k - 1]), round_down_px(xx[k]), w, x_off);
     return mask;
   }
   bool have_pos = false;
@@ -138,7 +140,7 @@ BLCD_HD RowMask polygon_row(const PolyPx& P, int y, int w, int h, int rules, int
       if (xs < pos) xs = pos;
     }
     if (xe < xs) continue;
-    mask |= span_mask(xs, xe, w);
+    mask |= span_mask(xs, xe, w, x_off);
     pos = xe + 1; have_pos = true;
   }
   // apex extension: two sloped edges of the same direction meeting in an integer vertex on this row.  Integer tests come
@@ -169,10 +171,10 @@ BLCD_HD RowMask polygon_row(const PolyPx& P, int y, int w, int h, int rules, int
       float a1 = edge_x_at(cx0, cy0, cdx, y2), a2 = edge_x_at(ox0, oy0, odx, y2);
       if ((bot && cpos) || (top && !cpos)) {
         int s = round_up_px(BLCD_FADD(a1 > a2 ? a1 : a2, 1.0f));
-        if (s <= vx) mask |= span_mask(s, vx, w);
+        if (s <= vx) mask |= span_mask(s, vx, w, x_off);
       } else {
         int t = round_up_px(a1 < a2 ? a1 : a2) - 1;
-        if (t >= vx) mask |= span_mask(vx, t, w);
+        if (t >= vx) mask |= span_mask(vx, t, w, x_off);
       }
     }
   }
@@ -194,16 +196,19 @@ BLCD_HD void polygon_px(PolyPx& out, const DShape& sh, float px, float py, float
 }
 
 // ink mask of canvas row y (y-up canvas coordinate) for one body
-BLCD_HD RowMask body_row(const DShape& sh, float px, float py, float s, float c, int y, int world_w, int lcd_w, int lcd_h, int rules) {
+// lcd_w scales metres to pixels; the ink returned is that of columns [x_off, x_off + win_w) (win_w = 0: the whole frame)
+BLCD_HD RowMask body_row(const DShape& sh, float px, float py, float s, float c, int y, int world_w, int lcd_w, int lcd_h, int rules,
+                         int x_off = 0, int win_w = 0) {
+  const int cw = win_w > 0 ? win_w : lcd_w;
   const double ww = (double)world_w, lw = (double)lcd_w;
   if (sh.type == SH_CIRCLE) {
     const double r = (double)sh.radius;
     return ellipse_row(to_px((double)px - r, ww, lw), to_px((double)py - r, ww, lw), to_px((double)px + r, ww, lw),
-                       to_px((double)py + r, ww, lw), y, lcd_w);
+                       to_px((double)py + r, ww, lw), y, cw, x_off);
   }
   PolyPx P;
   polygon_px(P, sh, px, py, s, c, ww, lw);
-  return polygon_row(P, y, lcd_w, lcd_h, rules);
+  return polygon_row(P, y, cw, lcd_h, rules, 1, 0, x_off);
 }
 
 // Per-body raster setup, computed once per frame: integer box of a circle, or integer vertices of a polygon.  The
@@ -231,10 +236,11 @@ BLCD_HD void body_px(BodyPx& o, const DShape& sh, float px, float py, float s, f
   }
 }
 
-BLCD_HD RowMask body_px_row(const BodyPx& o, int y, int lcd_w, int lcd_h, int rules) {
+// win_w / x_off: the column window whose ink is returned (the whole frame when it fits one RowMask)
+BLCD_HD RowMask body_px_row(const BodyPx& o, int y, int win_w, int lcd_h, int rules, int x_off = 0) {
   if (y < o.y0 || y > o.y1) return 0u;   // outside the shape's rows: neither the ellipse nor the polygon rules draw anything
-  if (o.kind == SH_CIRCLE) return ellipse_row(o.x0, o.y0, o.x1, o.y1, y, lcd_w);
-  return polygon_row(o.P, y, lcd_w, lcd_h, rules, o.y0, o.y1);
+  if (o.kind == SH_CIRCLE) return ellipse_row(o.x0, o.y0, o.x1, o.y1, y, win_w, x_off);
+  return polygon_row(o.P, y, win_w, lcd_h, rules, o.y0, o.y1, x_off);
 }
 
 BLCD_HD RowMask row_bits_from_ink(RowMask ink, int lcd_w) {

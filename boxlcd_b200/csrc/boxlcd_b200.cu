@@ -263,8 +263,10 @@ constexpr int kRenderThreads = 256;
 typedef std::conditional<sizeof(RowMask) == 4, unsigned int, unsigned long long>::type RowInk;   // atomicOr operand type
 constexpr int kRenderMaxFrames = 32;   // frames per block (bounds the BodyPx staging area in shared memory)
 __host__ __device__ inline int render_frames_per_block(int lcd_h) { int f = kRenderThreads / lcd_h; return f < kRenderMaxFrames ? f : kRenderMaxFrames; }
+// One launch renders the column window [x_off, x_off + win_w) of every frame (win_w <= bits of a RowMask) into words
+// word_off .. of each output row of row_stride words; frames wider than a RowMask take one launch per window.
 __global__ void __launch_bounds__(kRenderThreads) k_render_poses(const DScene* scene_g, const float* poses, const uint32_t* variants, int64_t n,
-                                                                  int lcd_w, int lcd_h, uint32_t* bits) {
+                                                                  int lcd_w, int lcd_h, uint32_t* bits, int x_off, int win_w, int row_stride, int word_off) {
   extern __shared__ __align__(16) unsigned char rsm[];
   DScene* scp = reinterpret_cast<DScene*>(rsm);
   BodyPx* bp_all = reinterpret_cast<BodyPx*>(rsm + kSceneBytes);
@@ -336,15 +338,14 @@ __global__ void __launch_bounds__(kRenderThreads) k_render_poses(const DScene* s
         rem -= cnt;
       }
       const int y = lo + rem;
-      RowMask m = body_px_row(bp[b], y, lcd_w, lcd_h, sc.rules);
+      RowMask m = body_px_row(bp[b], y, win_w, lcd_h, sc.rules, x_off);
       if (m) atomicOr(&rowink[y], (RowInk)m);
     }
   }
   __syncthreads();
   if (!live) return;
-  const RowMask out = row_bits_from_ink((RowMask)rowink[lcd_h - 1 - R], lcd_w);
-  if (sizeof(RowMask) == 4) bits[w * lcd_h + R] = (uint32_t)out;
-  else for (int k = 0, lw = row_words(lcd_w); k < lw; ++k) bits[(w * lcd_h + R) * lw + k] = row_word(out, k);
+  const RowMask out = row_bits_from_ink((RowMask)rowink[lcd_h - 1 - R], win_w);
+  for (int k = 0, lw = row_words(win_w); k < lw; ++k) bits[(w * lcd_h + R) * row_stride + word_off + k] = row_word(out, k);
 }
 
 }  // namespace
@@ -811,7 +812,7 @@ int BLCD_P(render_poses_sized)(BLCD_PENV* h, const float* poses_dev, const uint3
   if (n == 0) return 0;
   if (lcd_w <= 0) lcd_w = h->scene.lcd_w;
   if (lcd_h <= 0) lcd_h = h->scene.lcd_h;
-  if (lcd_w > kRowBits) return fail("blcd_render_poses: frame too wide for the " BLCD_PROFILE_NAME " profile");
+  if (lcd_w > 1024) return fail("blcd_render_poses: frame width out of range (<= 1024)");
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (lcd_h > kRenderThreads) return fail("blcd_render_poses: frame height out of range");
@@ -822,10 +823,15 @@ int BLCD_P(render_poses_sized)(BLCD_PENV* h, const float* poses_dev, const uint3
     h->render_attr_set = true;
   }
   if (begin_timing(h, st)) return -1;
-  k_render_poses<<<(unsigned)((n + fpb - 1) / fpb), kRenderThreads, rsm_bytes, st>>>(h->scene_dev, poses_dev, variant_dev, n, lcd_w, lcd_h, lcd_bits_dev);
-  CK(cudaGetLastError());
+  const int row_stride = row_words(lcd_w);
+  for (int x_off = 0; x_off < lcd_w; x_off += kRowBits) {   // one launch per column window of kRowBits pixels
+    const int win_w = lcd_w - x_off < kRowBits ? lcd_w - x_off : kRowBits;
+    k_render_poses<<<(unsigned)((n + fpb - 1) / fpb), kRenderThreads, rsm_bytes, st>>>(h->scene_dev, poses_dev, variant_dev, n, lcd_w, lcd_h, lcd_bits_dev,
+                                                                                       x_off, win_w, row_stride, x_off / 32);
+    CK(cudaGetLastError());
+    h->launches += 1;
+  }
   if (end_timing(h, st)) return -1;
-  h->launches += 1;
   return 0;
 }
 

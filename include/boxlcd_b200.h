@@ -181,7 +181,9 @@ int blcd_step_host_wait(blcd_handle h, int32_t keep_in_flight);
  * of every dynamic body's b2Transform; variant_dev optional [N] uint32 bitmask selecting shape variant per body. */
 int blcd_render_poses(blcd_handle h, const float* poses_dev, const uint32_t* variant_dev, int64_t n, uint32_t* lcd_bits_dev, uint64_t stream);
 
-/* Same at an explicit frame size, lcd_render(width, height) (world_env.py:460-470); 0 = the scene's own size; lcd_w <= 32 (small profile) or 64. */
+/* Same at an explicit frame size, lcd_render(width, height) (world_env.py:460-470); 0 = the scene's own size.  Any width up to
+ * 1024 (frames wider than the profile's row mask are rendered as 32- or 64-pixel column windows, one launch each);
+ * output rows have BLCD_LCD_WORDS(lcd_w) words; lcd_h <= 256.  The reference's viewer asks for 8x the env's size. */
 int blcd_render_poses_sized(blcd_handle h, const float* poses_dev, const uint32_t* variant_dev, int64_t n, int32_t lcd_w, int32_t lcd_h,
                             uint32_t* lcd_bits_dev, uint64_t stream);
 

@@ -21,7 +21,7 @@
 #include <string.h>
 
 #define LCD_MAX_VERTS 8
-#define LCD_MAX_W 64
+#define LCD_MAX_W 256
 
 typedef struct {
   int32_t kind;  /* 0 circle, else polygon */

@@ -21,13 +21,14 @@ ENVS = ['Dropbox', 'Bounce2', 'Object2', 'Urchin', 'Luxo', 'UrchinCube', 'LuxoCu
 
 
 def pack_bits(lcd):
-  """[H, W] bool -> [H] uint32, or [H, 2] (word k = pixels 32k .. 32k+31) for frames wider than 32 px"""
+  """[H, W] bool -> [H] uint32, or [H, ceil(W / 32)] (word k = pixels 32k .. 32k+31) for frames wider than 32 px"""
   H, W = lcd.shape
   if W <= 32:
     return (lcd.astype(np.uint64) << np.arange(W, dtype=np.uint64)[None]).sum(1).astype(np.uint32)
-  pad = np.zeros((H, 64), np.uint64)
+  lw = (W + 31) // 32
+  pad = np.zeros((H, 32 * lw), np.uint64)
   pad[:, :W] = lcd
-  return (pad.reshape(H, 2, 32) << np.arange(32, dtype=np.uint64)).sum(2).astype(np.uint32)
+  return (pad.reshape(H, lw, 32) << np.arange(32, dtype=np.uint64)).sum(2).astype(np.uint32)
 
 
 def shape_row(body):
@@ -87,6 +88,18 @@ def main(n_per_env=600, seed=0):
     out[f'{name}_bits'] = np.asarray(bits, np.uint32)
     out[f'{name}_meta'] = np.asarray([env.WIDTH, int(env.G.lcd_base * env.G.wh_ratio), env.G.lcd_base], np.int32)
     print(name, out[f'{name}_poses'].shape, 'ink mean', float(np.mean([bin(int(b)).count('0') for b in np.asarray(bits).ravel()[:64]])))
+  # the x8 view the reference's human renderer asks for (world_env.py:525: lcd_render(width * 8, height * 8)), mode '1'
+  for name, n8 in [('Urchin', 60), ('LuxoCube', 60)]:
+    env = boxLCD.env_map[name]()
+    env.seed(seed)
+    env.reset()
+    bodies = list(env.dynbodies.values())
+    W8, H8 = int(env.G.lcd_base * env.G.wh_ratio) * 8, env.G.lcd_base * 8
+    poses = [random_poses(rng, env, len(bodies), i % 3) for i in range(n8)]
+    out[f'{name}_x8_poses'] = np.asarray(poses, F)
+    out[f'{name}_x8_bits'] = np.asarray([pack_bits(np.asarray(ref_harness.render_poses(env, p, W8, H8), bool)) for p in poses], np.uint32)
+    out[f'{name}_x8_meta'] = np.asarray([env.WIDTH, W8, H8], np.int32)
+    print(name, 'x8', out[f'{name}_x8_bits'].shape)
   import PIL
   out['pillow_version'] = np.asarray(PIL.__version__)
   np.savez_compressed(os.path.join(HERE, 'lcd_golden.npz'), **out)

@@ -247,9 +247,9 @@ def ref_envs():
   return boxLCD
 
 
-def render_poses(env, poses):
+def render_poses(env, poses, width=None, height=None):
   """poses: list of (px, py, sin, cos) fp32 per dynamic body, in env.dynbodies order (after one reset)."""
   for (name, body), (px, py, s, c) in zip(env.dynbodies.items(), poses):
     body.position = (px, py)
     body._sc = (F(s), F(c))
-  return env.lcd_render()
+  return env.lcd_render(width, height) if width else env.lcd_render()

@@ -139,16 +139,19 @@ void hostsim_render_poses(void* p, const float* poses, const uint32_t* variants,
   const DScene& sc = h->scene;
   if (lcd_w <= 0) lcd_w = sc.lcd_w;
   if (lcd_h <= 0) lcd_h = sc.lcd_h;
+  const int lw = row_words(lcd_w);
   for (int64_t w = 0; w < n; ++w)
-    for (int R = 0; R < lcd_h; ++R) {
-      RowMask ink = 0u;
-      uint32_t variant = variants ? variants[w] : 0u;
-      for (int b = 0; b < sc.nb; ++b) {
-        const float* q = poses + (w * sc.nb + b) * 4;
-        ink |= body_row(sc.body[b].shape[(variant >> b) & 1u], q[0], q[1], q[2], q[3], lcd_h - 1 - R, sc.world_w, lcd_w, lcd_h, sc.rules);
+    for (int R = 0; R < lcd_h; ++R)
+      for (int x_off = 0; x_off < lcd_w; x_off += kRowBits) {   // column windows of one RowMask, like blcd_render_poses_sized
+        const int win_w = lcd_w - x_off < kRowBits ? lcd_w - x_off : kRowBits;
+        RowMask ink = 0u;
+        uint32_t variant = variants ? variants[w] : 0u;
+        for (int b = 0; b < sc.nb; ++b) {
+          const float* q = poses + (w * sc.nb + b) * 4;
+          ink |= body_row(sc.body[b].shape[(variant >> b) & 1u], q[0], q[1], q[2], q[3], lcd_h - 1 - R, sc.world_w, lcd_w, lcd_h, sc.rules, x_off, win_w);
+        }
+        for (int k = 0; k < row_words(win_w); ++k) bits[(w * lcd_h + R) * lw + x_off / 32 + k] = row_word(row_bits_from_ink(ink, win_w), k);
       }
-      for (int k = 0, lw = row_words(lcd_w); k < lw; ++k) bits[(w * lcd_h + R) * lw + k] = row_word(row_bits_from_ink(ink, lcd_w), k);
-    }
 }
 
 }  // extern "C"

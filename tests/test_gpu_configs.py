@@ -155,11 +155,8 @@ def test_partial_and_empty_reset():
 def test_errors_are_loud():
   env = make_env('Urchin')
   v = vec(env, 8)
-  with pytest.raises(RuntimeError, match='too wide for the small profile'):
-    v.render(64, 32)
-  with pytest.raises(RuntimeError, match='too wide'):
-    poses, var = v.get_poses_dev()
-    v.render_poses_dev(poses, None, 40, 16)
+  with pytest.raises(RuntimeError, match='width out of range'):
+    v.render(2048, 32)
   with pytest.raises(IndexError):
     blcd.envs.Dropbox({'walls': 0})     # the reference indexes robots[0] for the scroll offset (world_env.py:382)
   with pytest.raises(NotImplementedError):

@@ -59,6 +59,25 @@ def test_frames_bit_exact_vs_oracle_many_poses(name):
   assert (bits == ref).all(), f'{(bits != ref).any(1).sum()} / {n} frames differ'
 
 
+@pytest.mark.parametrize('name', ['Urchin', 'LuxoCube'])
+def test_human_view_size_frames_bit_exact_vs_reference_golden(name, monkeypatch):
+  """lcd_render(width * 8, height * 8): 256 x 128 / 192 x 128 frames, rendered as column windows by both profiles"""
+  gold = np.load(GOLD)
+  _, w8, h8 = [int(x) for x in gold[f'{name}_x8_meta']]
+  poses = torch.as_tensor(gold[f'{name}_x8_poses']).cuda()
+  for prof in ('small', 'large'):
+    monkeypatch.setenv('BLCD_PROFILE', prof)
+    v = vec(make_env(name), 1)
+    bits = v.render_poses_dev(poses, None, w8, h8).cpu().numpy().view(np.uint32)
+    assert bits.shape == gold[f'{name}_x8_bits'].shape and (bits == gold[f'{name}_x8_bits']).all(), prof
+    assert v.unpack_lcd(torch.as_tensor(bits.view(np.int32)).cuda(), w8).shape == (len(poses), h8, w8)
+  monkeypatch.delenv('BLCD_PROFILE')
+  env = make_env(name)
+  env.reset()
+  big = env.lcd_render(w8, h8)              # the single-env call the reference's viewer makes
+  assert big.shape == (h8, w8) and big.dtype == bool and (~big).sum() > 100
+
+
 def test_render_at_other_sizes_matches_oracle():
   env = make_env('Urchin')
   sp = env.layout.spec

@@ -70,6 +70,18 @@ def test_host_rasterizer_matches_reference_golden_frames():
     assert bits.shape == gold[f'{name}_bits'].shape and (bits == gold[f'{name}_bits']).all(), name
 
 
+@pytest.mark.parametrize('profile', ['small', 'large'])
+def test_host_rasterizer_at_the_human_view_size(profile):
+  """frames wider than one row mask are rendered as column windows (32 px small profile, 64 px large): x8 reference frames"""
+  import os
+  gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'lcd_golden.npz'))
+  for name in ['Urchin', 'LuxoCube']:
+    hs = HostSim(make_env(name).layout.spec, 1, profile=profile)
+    _, w8, h8 = [int(x) for x in gold[f'{name}_x8_meta']]
+    bits = hs.render_poses(gold[f'{name}_x8_poses'], None, w8, h8)
+    assert bits.shape == gold[f'{name}_x8_bits'].shape and (bits == gold[f'{name}_x8_bits']).all(), name
+
+
 @pytest.mark.parametrize('name', ['Urchin', 'LuxoCubes', 'Object3', 'UrchinBall'])
 def test_large_profile_build_is_bit_identical_on_small_scenes(name):
   """the two scene-size profiles (csrc/blcd_profile.h) are the same source with different limits: same results"""

@@ -27,6 +27,19 @@ def test_oracle_matches_reference_golden_frames(gold, env):
   assert (~oracle.unpack_bits(bits, lcd_w)).any(), 'frames are empty'
 
 
+@pytest.mark.parametrize('env', ['Urchin', 'LuxoCube'])
+def test_oracle_matches_reference_at_the_human_view_size(gold, env):
+  """lcd_render(width * 8, height * 8) (world_env.py:525), mode '1': 256 x 128 / 192 x 128 frames of the unmodified renderer"""
+  import boxlcd_b200 as blcd
+  sp = blcd.env_map[env]().layout.spec
+  ow = oracle.OracleWorlds(sp, 1)
+  ow.reset()
+  world_w, w8, h8 = [int(x) for x in gold[f'{env}_x8_meta']]
+  bits = oracle.lcd_render(ow.lcd_shapes(0), gold[f'{env}_x8_poses'], world_w, w8, h8)
+  assert bits.shape == gold[f'{env}_x8_bits'].shape and (bits == gold[f'{env}_x8_bits']).all()
+  assert (~oracle.unpack_bits(bits, w8)).sum() > 100 * len(bits)
+
+
 @pytest.mark.reference
 @pytest.mark.parametrize('env', ['Urchin', 'LuxoCube', 'UrchinBall', 'Object2', 'CrabCube'])
 def test_oracle_matches_live_reference(env):
