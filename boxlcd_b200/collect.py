@@ -79,8 +79,10 @@ def collect_arrays(env, n_rollouts, T, batch=65536, seed=0, device=None, world_o
   from boxlcd_b200.vec_env import VecWorldEnv
   S, A, P = env.obs_size, env.act_size, max(env.pobs_size, 1)
   H, W = env.observation_space.spaces['lcd'].shape
-  out = {'action': np.zeros((n_rollouts, T, A), np.float64), 'full_state': np.zeros((n_rollouts, T, S), np.float32),
-         'proprio': np.zeros((n_rollouts, T, P), np.float32), 'lcd': np.zeros((n_rollouts, T, H, W), np.bool_)}
+  # np.empty: every element is written below; the copies land straight in these arrays (no intermediate host tensors)
+  out = {'action': np.empty((n_rollouts, T, A), np.float64), 'full_state': np.empty((n_rollouts, T, S), np.float32),
+         'proprio': np.empty((n_rollouts, T, P), np.float32), 'lcd': np.empty((n_rollouts, T, H, W), np.bool_)}
+  pidx = torch.as_tensor(np.asarray(env.pobs_idxs, np.int64)) if env.pobs_size else None
   done, t0 = 0, time.time()
   vec = None
   while done < n_rollouts:
@@ -94,11 +96,16 @@ def collect_arrays(env, n_rollouts, T, batch=65536, seed=0, device=None, world_o
       vec = VecWorldEnv(env, n, device=device, seed=seed, world_offset=world_offset + done)
     vec.reset_dev()
     r = vec.rollout_dev(T)
-    out['action'][done:done + n] = r['action'].cpu().numpy()
-    fs = r['full_state'].cpu().numpy()
-    out['full_state'][done:done + n] = fs
-    out['proprio'][done:done + n] = fs[..., env.pobs_idxs] if env.pobs_size else 0.0
-    out['lcd'][done:done + n] = vec.unpack_lcd(r['lcd_bits']).cpu().numpy()
+    # conversions (f32 -> f64 actions, proprio gather, bit unpacking) run on the GPU; each result is copied directly into
+    # its slice of the output array
+    sl = slice(done, done + n)
+    torch.from_numpy(out['action'][sl]).copy_(r['action'].double())
+    torch.from_numpy(out['full_state'][sl]).copy_(r['full_state'])
+    if pidx is not None:
+      torch.from_numpy(out['proprio'][sl]).copy_(r['full_state'].index_select(2, pidx.to(r['full_state'].device)))
+    else:
+      out['proprio'][sl] = 0.0
+    torch.from_numpy(out['lcd'][sl]).copy_(vec.unpack_lcd(r['lcd_bits']))
     done += n
     if progress:
       progress(done, n_rollouts, done * T / (time.time() - t0))

@@ -19,7 +19,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
-CHUNK = 8 << 20
+CHUNK = 1 << 20   # independent deflate units: small enough that one 1000-rollout barrel (~80 MB) keeps every core busy
 
 
 # -- crc32 of a concatenation from the parts' crcs (zlib's crc32_combine, GF(2) matrix method) --------------------------------
