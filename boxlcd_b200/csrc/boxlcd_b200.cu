@@ -382,6 +382,9 @@ size_t smem_bytes(const BLCD_PENV* h, int block) { return (size_t)kSceneBytes + 
 template <typename F>
 int launch_sized(BLCD_PENV* h, F f) {
   switch (h->block) {
+#if BLCD_PROFILE_ID == 0
+    case 64: return f(std::integral_constant<int, 64>());
+#endif
     case 128: return f(std::integral_constant<int, 128>());
     case 256: return f(std::integral_constant<int, 256>());
 #if BLCD_PROFILE_ID == 0   // the large profile is only ever launched with 256 threads (or 128 as the shared-memory fallback)
@@ -442,8 +445,16 @@ int BLCD_P(create)(const blcd_spec* spec_host, int64_t n_worlds, int device, uin
   //    448-thread blocks instead of two of 256 (+33 %), 262 144 take 4 waves instead of 7 (+17 %).
   int sm_count = 148;
   CK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+  //  * few worlds (less than one 256-thread block per SM): smaller blocks, so that more SMs have one -- a block's time
+  //    shrinks only a little with its size (128 threads: 0.83 of 256), but 4 096 worlds then use 64 SMs instead of 16.
   h->block = 256;
-  if (h->scene.nj == 0) {
+  if (n_worlds <= (int64_t)sm_count * 128) {
+#if BLCD_PROFILE_ID == 0
+    h->block = n_worlds <= (int64_t)sm_count * 64 ? 64 : 128;
+#else
+    h->block = 128;
+#endif
+  } else if (h->scene.nj == 0) {
     const int sizes[] = {256, 320, 384, 448, 512};
     const double rel[] = {1.00, 1.09, 1.175, 1.26, 1.35};
     double best = 0.0;
@@ -457,7 +468,7 @@ int BLCD_P(create)(const blcd_spec* spec_host, int64_t n_worlds, int device, uin
   if (const char* e = getenv("BLCD_BLOCK")) h->block = atoi(e);
   {
 #if BLCD_PROFILE_ID == 0
-    const int sizes[] = {512, 448, 384, 320, 256, 128};
+    const int sizes[] = {512, 448, 384, 320, 256, 128, 64};
 #else
     const int sizes[] = {256, 128};
 #endif
