@@ -438,8 +438,8 @@ int BLCD_P(create)(const blcd_spec* spec_host, int64_t n_worlds, int device, uin
   // One block per SM (the register file is the occupancy limit) whose warps walk the solver phases together
   // (Sim::phase_align).  A launch therefore takes waves x (time of one block), waves = ceil(blocks / SMs).
   //  * articulated scenes: 256 threads.  Below 253 registers per thread the joint records spill, and a block's time grows
-  //    almost as fast as its size (Urchin, relative to 256 threads: 320 1.21, 384 1.37, 448 1.74, 512 1.82; LuxoCube loses
-  //    8 % at 384), so fewer, larger waves do not pay.
+  //    almost as fast as its size (Urchin at four full waves: 384 threads take 1.43x as long as 256 for 1.5x the worlds,
+  //    i.e. +5 %; Luxo +4 %; LuxoCube -8 %), so larger blocks are not worth their partly filled last wave.
   //  * joint-free scenes (balls, boxes): a block's time grows slowly with its size (Bounce2: 448 threads 1.26), so the size
   //    with the smallest waves x time estimate for this world count wins -- 65 536 Bounce2 worlds fit ONE wave of
   //    448-thread blocks instead of two of 256 (+33 %), 262 144 take 4 waves instead of 7 (+17 %).
