@@ -5,7 +5,8 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'
 import torch
 import boxlcd_b200 as b
 from boxlcd_b200.vec_env import VecWorldEnv
-v = VecWorldEnv(b.envs.Urchin(), 37888, seed=0)
+name = sys.argv[1] if len(sys.argv) > 1 else 'Urchin'
+v = VecWorldEnv(b.env_map[name](), 37888, seed=0)
 v.reset_dev()
 v.rollout_dev(20)
 v.rollout_dev(3)
