@@ -1,7 +1,7 @@
 """Scores 64 variants of Pillow's scanline polygon fill against the reference's recorded robot episodes (poses from the oracle replay,
 pixels from the gif frames) to find the rule set of the Pillow the recordings were made with; see tests/test_gif_episodes.py."""
 import sys, itertools, math
-sys.path.insert(0,'/root/repo/tests'); sys.path.insert(0,'/root/repo')
+import os; HERE = os.path.dirname(os.path.abspath(__file__)); sys.path.insert(0, os.path.dirname(HERE)); sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import numpy as np, boxlcd_b200 as blcd
 from oracle import oracle
 import test_gif_episodes as T

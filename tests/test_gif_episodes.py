@@ -125,7 +125,7 @@ def test_cubes_episode_under_both_box2d_rule_sets():
 # reference reset() with gym 0.17.3's seeding for the initial poses and stores the action sequence.  Frames were rendered
 # by the author's Pillow (requirements.txt pins 9.0.1), whose polygon fill differs from today's in a few pixels of thin
 # limbs: the replay uses the 'pil9' rule set (no overlap bookkeeping between spans, no apex extension, horizontal edges not
-# drawn -- the variant that explains most recorded frames out of 64 tried, tools/raster_rule_search.py).  A frame counts as
+# drawn -- the variant that explains most recorded frames out of 64 tried, tests/golden/raster_rule_search.py).  A frame counts as
 # reproduced when it is bit-exact; the others must stay within a handful of pixels.  UrchinCube is bit-exact for its first
 # 125 frames (12.5 s); where episodes leave the recording they do so late and gradually, as last-bit libm differences
 # (sinf / cosf of the author's glibc) are amplified by the contact dynamics.
