@@ -1,6 +1,6 @@
 """Run on ANY machine that has the real reference stack (pip install Box2D==2.3.10 gym==0.17.3 Pillow numpy, plus the
-boxLCD repo on PYTHONPATH) to produce physics golden vectors this repo cannot generate itself (pybox2d is not installable
-in the build image, so the physics oracle is "parity unpinned" until such a file is checked in).
+boxLCD repo on PYTHONPATH) to produce single-step physics golden vectors this repo cannot generate itself (pybox2d is not installable
+in the build image; the physics is pinned there through the reference's recorded episodes instead, tests/test_gif_episodes.py).
 
   python tools/dump_pybox2d_golden.py --out tests/golden/pybox2d_steps.npz [--n 256]
 
