@@ -7,8 +7,9 @@ in the build image; the physics is pinned there through the reference's recorded
 Protocol (last paragraph): for each env, sample a state with the reference reset, read it back as
 full_state s0, then `env.reset(full_state=s0); obs1 = env.step(a)`: a fresh b2World, no hidden warm-start history.
 Stored per env: s0 [n, S], action [n, A], s1 [n, S], lcd1 [n, H, W], raw body states before/after [n, B, 6]
-(x, y, angle, vx, vy, omega), and Box2D / Pillow versions.  tests/test_pybox2d_golden.py (skipped while the file is
-absent) replays the same protocol through the oracle and the CUDA path.
+(x, y, angle, vx, vy, omega), and Box2D / Pillow versions.  Replaying robots from such a file needs care: a joint's
+reference angle is fixed by the poses reset() SAMPLED before full_state was applied (pybox2d sets it when the joint is
+defined), so it can differ by a multiple of 2 pi from what b0 alone implies.
 """
 import argparse
 import numpy as np
