@@ -269,6 +269,24 @@ class VecWorldEnv:
     bits = self.render_poses_dev(poses, variants, width, height)
     return self.unpack_lcd(bits, width).cpu().numpy()
 
+  def render_rgb(self, width=None, height=None, idxs=None):
+    """lcd_render(width, height, lcd_mode='RGB') for the listed worlds (None = all) -> uint8 [n, height, width, 3].
+    Host Pillow over the device poses (boxlcd_b200/rgb_render.py)."""
+    from boxlcd_b200 import rgb_render
+    width = width or self.W
+    height = height or self.H
+    poses, variants = self.get_poses_dev()
+    poses, variants = poses.cpu().numpy(), variants.cpu().numpy()
+    sel = range(self.n) if idxs is None else list(idxs)
+    cache = {}
+    out = np.empty((len(sel), height, width, 3), np.uint8)
+    for k, i in enumerate(sel):
+      var = int(variants[i])
+      if var not in cache:
+        cache[var] = rgb_render.body_shapes(self.spec, var)
+      out[k] = rgb_render.render_rgb(cache[var], poses[i], self.env.WIDTH, width, height)
+    return out
+
 
 class AsyncVectorEnv(VecWorldEnv):
   """Constructor shape of the reference's `research/wrappers/async_vector_env.AsyncVectorEnv(env_fns, ...)`: callers such as

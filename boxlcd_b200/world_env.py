@@ -134,18 +134,54 @@ class WorldEnv:
     return {'full_state': obs['full_state'][0].astype(np.float64), 'proprio': obs['proprio'][0].astype(np.float64), 'lcd': obs['lcd'][0]}
 
   def lcd_render(self, width=None, height=None, lcd_mode='1'):
-    """world_env.py:460-512.  Mode '1' at any size is rendered by the CUDA rasterizer."""
+    """world_env.py:460-512.  Mode '1' at any size is rendered by the CUDA rasterizer; mode 'RGB' (the viewer's colour
+    picture, world_env.py:481-483,509-511) is drawn on the host with Pillow from the simulator's body transforms
+    (boxlcd_b200/rgb_render.py)."""
     lcd_mode = lcd_mode.upper()
     assert lcd_mode in ['1', 'RGB'], 'lcd_mode must be in one of these PIL supported modes'
     if width is None and height is None:
       width = int(self.G.lcd_base * self.G.wh_ratio)
       height = self.G.lcd_base
     if lcd_mode == 'RGB':
-      raise NotImplementedError('lcd_mode="RGB" (human viewer colours, world_env.py:481-483) is outside the hot path and not built')
+      return self._sim().render_rgb(width, height)[0]
     return self._sim().render(width, height)[0]
 
   def render(self, mode='rgb_array', lcd_mode='1', return_pyglet_view=False):
-    """world_env.py:514-535; only the array path is built (the pyglet viewer is UI, out of scope)."""
-    if mode != 'rgb_array':
-      raise NotImplementedError("render(mode='human') needs the pyglet viewer, which is out of scope")
-    return self.lcd_render(lcd_mode=lcd_mode)
+    """world_env.py:514-535.  mode='human' composes [8x colour view | 1 px | LCD frame x8] (world_env.py:525-531).  With
+    `return_pyglet_view` the composed picture itself is returned (the reference reads the same pixels back from the
+    window's colour buffer, viewer.py:31-36); showing it in a window needs pyglet, which is imported only then."""
+    from boxlcd_b200 import rgb_render
+    lcd_mode = lcd_mode.upper()
+    width = int(self.G.lcd_base * self.G.wh_ratio)
+    height = self.G.lcd_base
+    lcd = self.lcd_render(width, height, lcd_mode=lcd_mode)
+    if mode == 'rgb_array':
+      return lcd
+    elif mode == 'human':
+      high_res = self.lcd_render(width * 8, height * 8, lcd_mode='RGB').astype(np.uint8)
+      img = rgb_render.human_frame(high_res, lcd)
+      try:
+        import pyglet  # noqa: F401
+      except ImportError:
+        if return_pyglet_view:
+          return img
+        raise ImportError("render(mode='human') shows a window and needs pyglet; pass return_pyglet_view=True to get the composed picture instead")
+      if self.viewer is None:
+        self.viewer = _Viewer(width * 8, height * 8)
+      self.viewer.render(img)
+      return img if return_pyglet_view else lcd
+
+
+class _Viewer:
+  """viewer.py:4-37: a pyglet window that blits an already rendered picture"""
+  def __init__(self, width, height):
+    import pyglet
+    self.pyglet = pyglet
+    self.window = pyglet.window.Window(2 * width, height)
+
+  def render(self, image):
+    self.window.clear()
+    self.window.switch_to()
+    self.window.dispatch_events()
+    self.pyglet.image.ImageData(image.shape[1], image.shape[0], 'RGB', image.tobytes(), pitch=image.shape[1] * -3).blit(0, 0)
+    self.window.flip()

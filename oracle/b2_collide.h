@@ -4,7 +4,7 @@
  * (`Box2D/Collision/Shapes/b2{Circle,Edge,Polygon}Shape.cpp`, `b2CollideCircle.cpp`, `b2CollidePolygon.cpp`,
  * `b2CollideEdge.cpp`, `b2Collision.cpp`, `b2Distance.cpp`, `b2TimeOfImpact.cpp`) -- the C++ that pybox2d 2.3.10 wraps
  * and the reference calls through `b2World.Step` (boxLCD/world_env.py:446-452).  Box2D is not vendored in
- * /root/reference and pybox2d is not installable here: PARITY UNPINNED (see oracle/README.md).
+ * /root/reference and pybox2d is not installable here: parity is pinned through the reference's recorded episodes instead (tests/test_gif_hires.py; see oracle/README.md).
  */
 #pragma once
 #include "b2_math.h"

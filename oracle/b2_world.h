@@ -5,7 +5,10 @@
  * continuous collision against static bodies.  Restated from upstream Box2D 2.3.x `Dynamics/b2World.cpp`,
  * `b2Island.cpp`, `b2ContactManager.cpp`, `Contacts/b2Contact.cpp`, `Contacts/b2ContactSolver.cpp`,
  * `Joints/b2RevoluteJoint.cpp`, `b2Body.cpp`, `b2Fixture.cpp`, `Collision/b2BroadPhase.cpp`, `b2DynamicTree.cpp`.
- * PARITY UNPINNED: pybox2d cannot be run in this image (see oracle/README.md).
+ * Parity: pybox2d cannot be run in this image, so there are no fp32 state vectors from it; the restatement is pinned
+ * against what pybox2d DID produce -- the reference's recorded episodes (assets/envs/*.gif), replayed frame by frame at
+ * LCD resolution (tests/test_gif_episodes.py) and at the 8x colour resolution of the same frames (0.039 m per pixel,
+ * tests/test_gif_hires.py), up to the oracle's own one-ulp chaos horizon.  See oracle/README.md.
  *
  * One fixture per body (all the reference ever creates).  The dynamic tree is replaced by a brute-force scan over fat
  * AABBs: the set of pairs it reports is the same, and Box2D sorts the pair buffer by proxy id before creating contacts,

@@ -8,7 +8,8 @@ What runs for real: reference `WorldEnv.__init__` (spaces / key order), `reset()
 Pillow.  What is stubbed: pybox2d (`Box2D`), `gym`, `pyglet` -- none of them is installed here.
 The Box2D stub records bodies/joints and implements only `b2Transform * v` (fp32, separately rounded
 mul/add, as the x86 build of `b2Mul(b2Transform, b2Vec2)` does).  `b2World.Step` is a no-op: the
-physics itself is NOT covered by this harness (see oracle/README.md, "parity unpinned").
+physics itself is NOT covered by this harness; it is pinned against the recorded pybox2d episodes (tests/test_gif_hires.py,
+tests/test_gif_episodes.py; oracle/README.md).
 """
 import sys
 import types
