@@ -9,10 +9,10 @@ LIB_PATH = os.environ.get('BLCD_LIB') or os.path.join(HERE, 'libboxlcd_b200.so')
 CSRC = os.path.join(HERE, 'csrc')
 _lib = None
 
-SYMBOLS = ['blcd_last_error', 'blcd_version', 'blcd_create', 'blcd_destroy', 'blcd_reset', 'blcd_step', 'blcd_step_observe', 'blcd_observe',
-           'blcd_rollout', 'blcd_step_host', 'blcd_pin_host', 'blcd_step_host_async', 'blcd_step_host_wait', 'blcd_render_poses', 'blcd_render_poses_sized', 'blcd_set_bodies', 'blcd_get_bodies', 'blcd_get_poses', 'blcd_check_finite',
+SYMBOLS = ['blcd_last_error', 'blcd_version', 'blcd_create', 'blcd_destroy', 'blcd_rekey', 'blcd_reset', 'blcd_step', 'blcd_step_observe', 'blcd_observe',
+           'blcd_rollout', 'blcd_step_host', 'blcd_pin_host', 'blcd_unpin_host', 'blcd_step_host_async', 'blcd_step_host_wait', 'blcd_render_poses', 'blcd_render_poses_sized', 'blcd_set_bodies', 'blcd_get_bodies', 'blcd_get_poses', 'blcd_check_finite',
            'blcd_state_bytes', 'blcd_save_state', 'blcd_load_state', 'blcd_num_worlds', 'blcd_kernel_launches', 'blcd_last_step_ms',
-           'blcd_enable_timing', 'blcd_get_counters', 'blcd_scene_info']
+           'blcd_enable_timing', 'blcd_get_counters', 'blcd_scene_info', 'blcd_measure_peaks']
 
 
 def build(force=False):
@@ -36,6 +36,7 @@ def lib():
   l.blcd_last_error.restype = C.c_char_p
   l.blcd_create.argtypes = [vp, i64, C.c_int, u64, i64, C.POINTER(vp)]
   l.blcd_destroy.argtypes = [vp]
+  l.blcd_rekey.argtypes = [vp, u64, i64]
   l.blcd_reset.argtypes = [vp, vp, i64, vp, u64]
   l.blcd_step.argtypes = [vp, vp, vp, u64]
   l.blcd_step_observe.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, u64]
@@ -43,6 +44,7 @@ def lib():
   l.blcd_rollout.argtypes = [vp, i32, vp, vp, vp, u64]
   l.blcd_step_host.argtypes = [vp, vp, vp, vp, vp]
   l.blcd_pin_host.argtypes = [vp, vp, i64]
+  l.blcd_unpin_host.argtypes = [vp, vp]
   l.blcd_step_host_async.argtypes = [vp, vp, vp, vp, vp]
   l.blcd_step_host_wait.argtypes = [vp, i32]
   l.blcd_render_poses.argtypes = [vp, vp, vp, i64, vp, u64]
@@ -63,6 +65,7 @@ def lib():
   l.blcd_enable_timing.argtypes = [vp, C.c_int]
   l.blcd_get_counters.argtypes = [vp, vp, u64]
   l.blcd_scene_info.argtypes = [vp, vp]
+  l.blcd_measure_peaks.argtypes = [C.c_int, C.POINTER(C.c_double)]
   _lib = l
   return l
 

@@ -39,7 +39,7 @@ extern "C" {
 
 int blcd_fail_msg(const char* msg) { g_err = msg ? msg : ""; return -1; }
 const char* blcd_last_error(void) { return g_err.c_str(); }
-int blcd_version(void) { return 110; }
+int blcd_version(void) { return 120; }
 
 int blcd_create(const blcd_spec* spec_host, int64_t n_worlds, int device, uint64_t seed, int64_t world_offset, blcd_handle* out) {
   if (!spec_host || !out || n_worlds <= 0) return blcd_fail_msg("blcd_create: bad arguments");
@@ -64,6 +64,10 @@ int blcd_destroy(blcd_handle h) {
   return rc;
 }
 
+int blcd_rekey(blcd_handle h, uint64_t seed, int64_t world_offset) {
+  BLCD_NEED(h, "blcd_rekey");
+  return BLCD_FWD(rekey, seed, world_offset);
+}
 int blcd_reset(blcd_handle h, const int64_t* idx_dev, int64_t n, const float* full_state_dev, uint64_t stream) {
   BLCD_NEED(h, "blcd_reset");
   return BLCD_FWD(reset, idx_dev, n, full_state_dev, stream);
@@ -93,6 +97,10 @@ int blcd_step_host(blcd_handle h, const float* actions_host, float* full_state_h
 int blcd_pin_host(blcd_handle h, const void* buf_host, int64_t bytes) {
   BLCD_NEED(h, "blcd_pin_host");
   return BLCD_FWD(pin_host, buf_host, bytes);
+}
+int blcd_unpin_host(blcd_handle h, const void* buf_host) {
+  BLCD_NEED(h, "blcd_unpin_host");
+  return BLCD_FWD(unpin_host, buf_host);
 }
 int blcd_step_host_async(blcd_handle h, const float* actions_host, float* full_state_host, uint32_t* lcd_bits_host, uint8_t* done_host) {
   BLCD_NEED(h, "blcd_step_host_async");

@@ -13,6 +13,7 @@ int blcd_fail_msg(const char* msg);   // records the calling thread's error mess
 
 int BLCD_P(create)(const blcd_spec* spec_host, int64_t n_worlds, int device, uint64_t seed, int64_t world_offset, BLCD_PENV** out);
 int BLCD_P(destroy)(BLCD_PENV* h);
+int BLCD_P(rekey)(BLCD_PENV* h, uint64_t seed, int64_t world_offset);
 int BLCD_P(reset)(BLCD_PENV* h, const int64_t* idx_dev, int64_t n, const float* full_state_dev, uint64_t stream);
 int BLCD_P(step)(BLCD_PENV* h, const float* actions_dev, float* actions_out_dev, uint64_t stream);
 int BLCD_P(observe)(BLCD_PENV* h, float* full_state_dev, float* proprio_dev, uint32_t* lcd_bits_dev, uint8_t* lcd_bool_dev, uint8_t* done_dev,
@@ -22,6 +23,7 @@ int BLCD_P(step_observe)(BLCD_PENV* h, const float* actions_dev, float* actions_
 int BLCD_P(rollout)(BLCD_PENV* h, int32_t T, float* full_state_dev, uint32_t* lcd_bits_dev, float* actions_dev, uint64_t stream);
 int BLCD_P(step_host)(BLCD_PENV* h, const float* actions_host, float* full_state_host, uint32_t* lcd_bits_host, uint8_t* done_host);
 int BLCD_P(pin_host)(BLCD_PENV* h, const void* buf_host, int64_t bytes);
+int BLCD_P(unpin_host)(BLCD_PENV* h, const void* buf_host);
 int BLCD_P(step_host_async)(BLCD_PENV* h, const float* actions_host, float* full_state_host, uint32_t* lcd_bits_host, uint8_t* done_host);
 int BLCD_P(step_host_wait)(BLCD_PENV* h, int32_t keep_in_flight);
 int BLCD_P(render_poses)(BLCD_PENV* h, const float* poses_dev, const uint32_t* variant_dev, int64_t n, uint32_t* lcd_bits_dev, uint64_t stream);

@@ -367,8 +367,7 @@ struct BLCD_PENV {
   // pinned staging for blcd_step_host
   float* h_act = nullptr; float* h_fs = nullptr; uint32_t* h_bits = nullptr; uint8_t* h_done = nullptr;
   float* d_act = nullptr; float* d_fs = nullptr; uint32_t* d_bits = nullptr; uint8_t* d_done = nullptr;
-  std::vector<std::pair<const void*, size_t>> pinned;   // caller buffers page-locked by blcd_step_host
-  std::vector<std::pair<const void*, size_t>> pinned_user;   // ... and by blcd_pin_host
+  std::vector<std::pair<const void*, size_t>> pinned_user;   // caller buffers page-locked by blcd_pin_host
   cudaStream_t hstream[kHostStreams] = {};              // blcd_step_host's pipeline streams
   cudaEvent_t hev[kHostDepth][kHostStreams] = {};       // completion of host step s (ring) on each stream
   uint64_t host_submitted = 0, host_completed = 0;
@@ -479,29 +478,52 @@ int BLCD_P(create)(const blcd_spec* spec_host, int64_t n_worlds, int device, uin
       if (b <= h->block && smem_bytes(h, b) <= (size_t)smem_max) { h->block = b; break; }
   }
   if (smem_bytes(h, h->block) > (size_t)smem_max) { delete h; return fail("scene working set does not fit shared memory"); }
-  CK(cudaMalloc(&h->scene_dev, sizeof(DScene)));
-  CK(cudaMemcpy(h->scene_dev, &h->scene, sizeof(DScene), cudaMemcpyHostToDevice));
-  size_t bytes = (size_t)h->scene.state_words * (size_t)n_worlds * 4;
-  CK(cudaMalloc(&h->state, bytes));
-  CK(cudaMemset(h->state, 0, bytes));
-  k_init<<<(unsigned)((n_worlds + 255) / 256), 256>>>(h->scene_dev, h->state, n_worlds);
-  CK(cudaGetLastError());
-  CK(cudaDeviceSynchronize());
-  h->launches += 1;
-  CK(cudaEventCreate(&h->ev0));
-  CK(cudaEventCreate(&h->ev1));
-  int rc = launch_sized(h, [&](auto B) {
-    constexpr int BLOCK = decltype(B)::value;
-    size_t sb = smem_bytes(h, BLOCK);
-    if (set_smem_attr(k_reset<BLOCK>, sb)) return -1;
-    if (set_smem_attr(k_set_bodies<BLOCK>, sb)) return -1;
-    if (set_smem_attr(k_step<BLOCK>, sb)) return -1;
-    if (set_smem_attr(k_rollout<BLOCK>, sb)) return -1;
-    if (set_smem_attr(k_observe<BLOCK>, sb)) return -1;
-    return 0;
-  });
-  if (rc) return rc;
+  // everything below allocates device resources: a failure (e.g. out of memory for too many worlds) releases what was
+  // already allocated, so that a caller can retry with fewer worlds without leaking
+  int rc = [&]() -> int {
+    CK(cudaMalloc(&h->scene_dev, sizeof(DScene)));
+    CK(cudaMemcpy(h->scene_dev, &h->scene, sizeof(DScene), cudaMemcpyHostToDevice));
+    size_t bytes = (size_t)h->scene.state_words * (size_t)n_worlds * 4;
+    CK(cudaMalloc(&h->state, bytes));
+    CK(cudaMemset(h->state, 0, bytes));
+    k_init<<<(unsigned)((n_worlds + 255) / 256), 256>>>(h->scene_dev, h->state, n_worlds);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    h->launches += 1;
+    CK(cudaEventCreate(&h->ev0));
+    CK(cudaEventCreate(&h->ev1));
+    return launch_sized(h, [&](auto B) {
+      constexpr int BLOCK = decltype(B)::value;
+      size_t sb = smem_bytes(h, BLOCK);
+      if (set_smem_attr(k_reset<BLOCK>, sb)) return -1;
+      if (set_smem_attr(k_set_bodies<BLOCK>, sb)) return -1;
+      if (set_smem_attr(k_step<BLOCK>, sb)) return -1;
+      if (set_smem_attr(k_rollout<BLOCK>, sb)) return -1;
+      if (set_smem_attr(k_observe<BLOCK>, sb)) return -1;
+      return 0;
+    });
+  }();
+  if (rc) {
+    cudaGetLastError();          // clear the sticky-free error state before the frees
+    BLCD_P(destroy)(h);          // frees whatever was allocated (null members are skipped); keeps the recorded message
+    return rc;
+  }
   *out = h;
+  return 0;
+}
+
+// Re-key the handle's random streams: world w becomes global world world_offset + w of stream family `seed`.  Only the key
+// changes (and every world's draw counter restarts at zero, as in a fresh handle) -- the state buffer, the scene tables
+// and every allocation stay; the next blcd_reset samples from the new streams, so a re-keyed handle produces exactly
+// what a handle created with (seed, world_offset) would.  Lets a collector walk one allocation over a long dataset.
+int BLCD_P(rekey)(BLCD_PENV* h, uint64_t seed, int64_t world_offset) {
+  if (!h) return fail("blcd_rekey: null handle");
+  if (h->host_submitted != h->host_completed) return fail("blcd_rekey: host steps are still in flight");
+  CK(cudaSetDevice(h->device));
+  // draw counters are one [word][world] row of the state buffer
+  CK(cudaMemset(h->state + (size_t)(h->scene.off_misc + 3) * (size_t)h->n, 0, (size_t)h->n * 4));
+  h->seed = seed;
+  h->world_offset = world_offset;
   return 0;
 }
 
@@ -518,7 +540,6 @@ int BLCD_P(destroy)(BLCD_PENV* h) {
   if (h->h_bits) cudaFreeHost(h->h_bits);
   if (h->h_done) cudaFreeHost(h->h_done);
   cudaFree(h->d_act); cudaFree(h->d_fs); cudaFree(h->d_bits); cudaFree(h->d_done);
-  for (auto& r : h->pinned) cudaHostUnregister(const_cast<void*>(r.first));
   for (auto& r : h->pinned_user) cudaHostUnregister(const_cast<void*>(r.first));
   for (auto& ring : h->hev) for (auto& e : ring) if (e) cudaEventDestroy(e);
   delete h;
@@ -667,30 +688,23 @@ int BLCD_P(rollout)(BLCD_PENV* h, int32_t T, float* full_state_dev, uint32_t* lc
 // false if the driver refuses (then the call falls back to the handle's own pinned staging buffers)
 static bool is_pinned(const BLCD_PENV* h, const void* p, size_t bytes) {
   const char* q = static_cast<const char*>(p);
-  for (const auto* list : {&h->pinned, &h->pinned_user})
-    for (auto& r : *list) {
-      const char* base = static_cast<const char*>(r.first);
-      if (q >= base && q + bytes <= base + r.second) return true;
-    }
+  for (auto& r : h->pinned_user) {
+    const char* base = static_cast<const char*>(r.first);
+    if (q >= base && q + bytes <= base + r.second) return true;
+  }
   return false;
 }
 
-// keep = true: pinned on the caller's request (blcd_pin_host), stays until blcd_destroy; false: pinned on first use by
-// blcd_step_host, kept in a small most-recent list
-static bool pin_user_buffer(BLCD_PENV* h, const void* p, size_t bytes, bool keep = false) {
+// page-lock caller memory on the caller's explicit request (blcd_pin_host); it stays registered until blcd_unpin_host or
+// blcd_destroy, and the caller keeps it alive for that long
+static bool pin_user_buffer(BLCD_PENV* h, const void* p, size_t bytes) {
   if (!p) return false;
   if (is_pinned(h, p, bytes)) return true;
   if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) != cudaSuccess) {
     cudaGetLastError();
     return false;
   }
-  if (keep) { h->pinned_user.emplace_back(p, bytes); return true; }
-  if (h->pinned.size() >= 8) {   // keep the registry small: forget (and unpin) the oldest buffer -- once nothing is in flight
-    for (auto& st : h->hstream) if (st) cudaStreamSynchronize(st);
-    cudaHostUnregister(const_cast<void*>(h->pinned.front().first));
-    h->pinned.erase(h->pinned.begin());
-  }
-  h->pinned.emplace_back(p, bytes);
+  h->pinned_user.emplace_back(p, bytes);
   return true;
 }
 
@@ -770,10 +784,12 @@ int BLCD_P(step_host)(BLCD_PENV* h, const float* actions_host, float* full_state
   size_t na, nf, nb, nd;
   if (host_step_buffers(h, &na, &nf, &nb, &nd)) return -1;
   if (host_step_wait(h, 0)) return -1;   // earlier asynchronous steps first: the device-side staging area is shared
-  // caller buffers are page-locked in place once (then the copies are direct DMA transfers); if the driver refuses, the
-  // call goes through the handle's own pinned staging buffers
-  const bool pa = pin_user_buffer(h, actions_host, na), pf = pin_user_buffer(h, full_state_host, nf);
-  const bool pb = pin_user_buffer(h, lcd_bits_host, nb), pd = pin_user_buffer(h, done_host, nd);
+  // Buffers the caller page-locked with blcd_pin_host are copied to / from directly (DMA); anything else is staged
+  // through the handle's own pinned memory.  The call never page-locks caller memory itself: a Python caller passes
+  // fresh numpy arrays every step, and a registration that outlives its array would go stale when the allocator
+  // unmaps and re-uses the address.
+  const bool pa = actions_host && is_pinned(h, actions_host, na), pf = full_state_host && is_pinned(h, full_state_host, nf);
+  const bool pb = lcd_bits_host && is_pinned(h, lcd_bits_host, nb), pd = done_host && is_pinned(h, done_host, nd);
   if (actions_host && !pa) memcpy(h->h_act, actions_host, na);
   if (host_step_submit(h, actions_host ? (pa ? actions_host : h->h_act) : nullptr, full_state_host ? (pf ? full_state_host : h->h_fs) : nullptr,
                        lcd_bits_host ? (pb ? lcd_bits_host : h->h_bits) : nullptr, done_host ? (pd ? done_host : h->h_done) : nullptr,
@@ -789,8 +805,21 @@ int BLCD_P(step_host)(BLCD_PENV* h, const float* actions_host, float* full_state
 int BLCD_P(pin_host)(BLCD_PENV* h, const void* buf_host, int64_t bytes) {
   if (!h || !buf_host || bytes <= 0) return fail("blcd_pin_host: bad arguments");
   CK(cudaSetDevice(h->device));
-  if (!pin_user_buffer(h, buf_host, (size_t)bytes, true)) return fail("blcd_pin_host: the driver refused to page-lock this buffer");
+  if (!pin_user_buffer(h, buf_host, (size_t)bytes)) return fail("blcd_pin_host: the driver refused to page-lock this buffer");
   return 0;
+}
+
+int BLCD_P(unpin_host)(BLCD_PENV* h, const void* buf_host) {
+  if (!h || !buf_host) return fail("blcd_unpin_host: bad arguments");
+  CK(cudaSetDevice(h->device));
+  for (size_t i = 0; i < h->pinned_user.size(); ++i)
+    if (h->pinned_user[i].first == buf_host) {
+      if (host_step_wait(h, 0)) return -1;     // nothing may still be copying from / into it
+      CK(cudaHostUnregister(const_cast<void*>(buf_host)));
+      h->pinned_user.erase(h->pinned_user.begin() + i);
+      return 0;
+    }
+  return fail("blcd_unpin_host: this address was not registered with blcd_pin_host");
 }
 
 int BLCD_P(step_host_async)(BLCD_PENV* h, const float* actions_host, float* full_state_host, uint32_t* lcd_bits_host, uint8_t* done_host) {

@@ -30,7 +30,9 @@ class Box:
 
 class Dict:
   def __init__(self, spaces):
-    self.spaces = dict(spaces)
+    # gym 0.17.3 spaces.Dict sorts a plain dict's keys (gym/spaces/dict.py): callers that iterate `.spaces.items()`
+    # (examples/collect.py:28, research/data.py:50) see full_state, lcd, proprio -- and write npz members in that order
+    self.spaces = dict(sorted(dict(spaces).items()))
 
   def __getitem__(self, k):
     return self.spaces[k]

@@ -57,6 +57,15 @@ class VecWorldEnv:
     self.close()
     self._create(0 if seeds is None else int(seeds))
 
+  def rekey(self, seed=None, world_offset=None):
+    """blcd_rekey: keep every allocation, make world w the global world `world_offset + w` of stream family `seed`; the next
+    reset samples from those streams (as a freshly created VecWorldEnv with the same arguments would)."""
+    seed = self._seed if seed is None else int(seed)
+    world_offset = self.world_offset if world_offset is None else int(world_offset)
+    torch.cuda.current_stream(self.device).synchronize()
+    _lib.check(self.l.blcd_rekey(self.h, seed, world_offset))
+    self._seed, self.world_offset = seed, world_offset
+
   # -- lifetime -------------------------------------------------------------------------------------------------------
   def close(self):
     if getattr(self, 'h', None):
@@ -196,11 +205,14 @@ class VecWorldEnv:
   def unpack_lcd(self, bits, width=None):
     """packed rows -> bool [..., H, W] (True = background), the reference's `lcd` observation"""
     w = width or self.W
-    shifts = torch.arange(min(w, 32), device=bits.device, dtype=torch.int32)
-    if w <= 32:
-      return ((bits.unsqueeze(-1) >> shifts) & 1).to(torch.bool)
-    px = ((bits.unsqueeze(-1) >> shifts) & 1).to(torch.bool)     # [..., H, words, 32]
-    return px.reshape(px.shape[:-2] + (-1,))[..., :w]
+    # byte k of a little-endian row word holds pixels 8k .. 8k+7: unpack on uint8 views, so the only intermediate is one
+    # byte per pixel (an int32 shift-and-mask would need 4-8 bytes per pixel: tens of GB for a dataset-sized batch)
+    words = 1 if w <= 32 else bits.shape[-1]
+    lead = bits.shape[:-1] if w <= 32 else bits.shape[:-2]
+    by = bits.contiguous().view(torch.uint8).reshape(lead + (4 * words,))
+    shifts = torch.arange(8, device=bits.device, dtype=torch.uint8)
+    px = ((by.unsqueeze(-1) >> shifts) & 1).reshape(lead + (32 * words,))
+    return px[..., :w].to(torch.bool)
 
   def _obs_numpy(self, obs):
     return {'full_state': obs['full_state'].cpu().numpy(), 'proprio': obs['proprio'].cpu().numpy(),

@@ -104,7 +104,7 @@ typedef struct {
   double walls[BLCD_MAX_WALLS][4];         /* static edge shapes x1,y1,x2,y2 (world_env.py:311-314), creation order */
   double gravity[2];
   int32_t world_w, world_h;                /* WIDTH = int(wh_ratio*base_dim), HEIGHT = base_dim (world_env.py:144-150) */
-  int32_t lcd_w, lcd_h;                    /* frame size in pixels, lcd_w <= 32 */
+  int32_t lcd_w, lcd_h;                    /* frame size in pixels, lcd_w <= 64 (32 in the small profile, 64 in the large one) */
   int32_t obs_size, pobs_size, act_size;   /* pobs_size = 0 -> proprio is zeros(1) */
   int32_t pobs_index[BLCD_MAX_OBS];
   int32_t n_substeps;                      /* 3 when fps < 30 else 1 (world_env.py:446-452) */
@@ -130,6 +130,11 @@ int blcd_version(void);
  * so results do not depend on how worlds are sharded over handles / GPUs. */
 int blcd_create(const blcd_spec* spec_host, int64_t n_worlds, int device, uint64_t seed, int64_t world_offset, blcd_handle* out);
 int blcd_destroy(blcd_handle h);
+
+/* Re-key the random streams of an existing handle: world w becomes global world world_offset + w of stream family `seed`.
+ * Nothing is reallocated; the next blcd_reset samples from the new streams.  This is what lets one allocation walk over a
+ * long dataset (the reference's collector re-uses its worker processes across barrels, research/data.py:36-79). */
+int blcd_rekey(blcd_handle h, uint64_t seed, int64_t world_offset);
 
 /* reset(): idx_dev = NULL resets all worlds (n ignored), else the n listed worlds.  full_state_dev = NULL samples the
  * reference's reset distribution (world_env.py:197-304) from the per-world RNG; otherwise [n, obs_size] normalized
@@ -157,16 +162,16 @@ int blcd_rollout(blcd_handle h, int32_t T, float* full_state_dev, uint32_t* lcd_
 
 /* Host-buffer variant of step + observe (the call an unmodified reference-side caller would bind): copies actions
  * host->device, steps, observes, copies full_state and packed frames device->host, and synchronizes.
- * The caller's buffers are page-locked in place on first use (cudaHostRegister; the eight most recent buffers stay
- * registered until blcd_destroy) so that the copies are direct DMA transfers; if the driver refuses, the call stages
- * through pinned memory of its own.  Keep a buffer alive until the handle is destroyed or eight other buffers have been
- * used since. */
+ * Buffers that lie inside memory the caller page-locked with blcd_pin_host are copied to / from directly (DMA);
+ * any other buffer is staged through pinned memory owned by the handle, so ordinary pageable arrays (a fresh numpy
+ * array per step) are safe to pass.  The call never page-locks caller memory on its own. */
 int blcd_step_host(blcd_handle h, const float* actions_host, float* full_state_host, uint32_t* lcd_bits_host, uint8_t* done_host);
 
 /* The same split into submit and wait, the call shape of the reference's AsyncVectorEnv.step_async / step_wait
  * (research/wrappers/async_vector_env.py:131-242), for callers whose next actions do not depend on the step just
  * submitted (collect.py:35 samples actions independently of the observation; double-buffered RL):
  *   blcd_pin_host         page-locks caller memory once (a whole [T, N, ...] dataset array, or a ring of step buffers);
+ *                         the memory must stay allocated until blcd_unpin_host(same address) or blcd_destroy;
  *   blcd_step_host_async  enqueues one env step reading / writing buffers inside pinned memory and returns at once
  *                         (up to 3 further steps may be queued behind it; it blocks only when that queue is full);
  *   blcd_step_host_wait   returns when at most keep_in_flight submitted steps are unfinished; the outputs of every
@@ -174,6 +179,7 @@ int blcd_step_host(blcd_handle h, const float* actions_host, float* full_state_h
  * Each step still copies its actions host->device and its observations device->host; consecutive steps overlap only in
  * that the copies and the ragged kernel tail of one step hide behind the next step's kernel. */
 int blcd_pin_host(blcd_handle h, const void* buf_host, int64_t bytes);
+int blcd_unpin_host(blcd_handle h, const void* buf_host);
 int blcd_step_host_async(blcd_handle h, const float* actions_host, float* full_state_host, uint32_t* lcd_bits_host, uint8_t* done_host);
 int blcd_step_host_wait(blcd_handle h, int32_t keep_in_flight);
 
@@ -205,6 +211,12 @@ int blcd_load_state(blcd_handle h, const void* buf_dev, uint64_t stream);
 /* Failure detection: counts the worlds whose body state is no longer finite (NaN / inf after a diverged solve) and, if
  * invalid_dev != NULL ([N] uint8), flags them; the caller decides whether to blcd_reset those indices.  Synchronous. */
 int blcd_check_finite(blcd_handle h, uint8_t* invalid_dev, int64_t* n_invalid_host);
+
+/* Measured denominators for the solver roofline (bench.py): out4 = { lane-FMAs per second of the whole device with every
+ * issue slot filled (x2 = fp32 FLOP/s; = peak lane-instructions per second), FFMAs per second of ONE dependent chain
+ * (clock / dependent-issue latency: the regime of a serial Gauss-Seidel sweep), SM count, nominal max SM clock in Hz }.
+ * Synchronous; takes ~0.1 s. */
+int blcd_measure_peaks(int device, double* out4);
 
 /* Introspection used by tests and bench.py */
 int64_t blcd_num_worlds(blcd_handle h);

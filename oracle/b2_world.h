@@ -6,7 +6,7 @@
  * `b2Island.cpp`, `b2ContactManager.cpp`, `Contacts/b2Contact.cpp`, `Contacts/b2ContactSolver.cpp`,
  * `Joints/b2RevoluteJoint.cpp`, `b2Body.cpp`, `b2Fixture.cpp`, `Collision/b2BroadPhase.cpp`, `b2DynamicTree.cpp`.
  * Parity: pybox2d cannot be run in this image, so there are no fp32 state vectors from it; the restatement is pinned
- * against what pybox2d DID produce -- the reference's recorded episodes (assets/envs/*.gif), replayed frame by frame at
+ * against what pybox2d DID produce -- the reference's recorded episodes (assets/envs/<Env>.gif), replayed frame by frame at
  * LCD resolution (tests/test_gif_episodes.py) and at the 8x colour resolution of the same frames (0.039 m per pixel,
  * tests/test_gif_hires.py), up to the oracle's own one-ulp chaos horizon.  See oracle/README.md.
  *

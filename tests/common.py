@@ -27,5 +27,32 @@ def random_bodies(env, n, rng, speed=3.0):
   return b.astype(np.float32), variants
 
 
+def oracle_sensitivity(env, bodies, variants, act, copies=48, seed=1):
+  """How far the ORACLE's own single-step result moves when the inputs of a world are nudged by one fp32 ulp: for every
+  world [m] run `copies` oracle copies whose initial state differs from the original in 1-4 randomly chosen components by
+  one ulp, and return the largest relative deviation (position / angle) of any copy from the unnudged oracle.  Ordinary
+  worlds give ~1e-7; a world that sits on a discrete decision boundary (a contact appearing or not, a clip point changing
+  identity, a limit engaging, the block solver switching case, a TOI event) gives the size of the jump between the two
+  outcomes."""
+  from oracle import oracle
+  import os
+  sp = env.layout.spec
+  m = len(bodies)
+  rng = np.random.RandomState(seed)
+  b2 = np.repeat(bodies, copies, 0).copy()
+  for i in range(len(b2)):
+    if i % copies == 0:
+      continue
+    for _ in range(rng.randint(1, 5)):
+      b, k = rng.randint(sp.n_bodies), rng.randint(6)
+      v = b2[i, b, k]
+      b2[i, b, k] = np.nextafter(v, np.float32(v + (1 if rng.rand() < .5 else -1)), dtype=np.float32)
+  ow = oracle.OracleWorlds(sp, len(b2), threads=os.cpu_count() or 1)
+  ow.set_bodies(b2, None if variants is None else np.repeat(variants, copies))
+  ow.step(np.repeat(act, copies, 0))
+  o = ow.get_bodies().reshape(m, copies, sp.n_bodies, 6)
+  return rel_err(o[:, 1:, :, :3], o[:, :1, :, :3]).max((1, 2, 3))
+
+
 def rel_err(a, b, floor=1.0):
   return np.abs(a - b) / np.maximum(np.abs(b), floor)

@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
   for sym in sorted(declared):
     assert hasattr(l, sym), f'{sym} declared in include/boxlcd_b200.h but not exported'
   assert set(_lib.SYMBOLS) <= declared
-  assert l.blcd_version() == 110
+  assert l.blcd_version() >= 120
 
 
 def test_spec_struct_layout_matches_header():

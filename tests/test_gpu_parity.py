@@ -9,7 +9,7 @@ import pytest
 import torch
 import boxlcd_b200 as blcd
 from oracle import oracle
-from common import make_env, random_bodies, rel_err, ENVS_CORE
+from common import make_env, random_bodies, rel_err, oracle_sensitivity, ENVS_CORE
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), 'golden', 'lcd_golden.npz')
@@ -138,6 +138,21 @@ def test_single_env_step_within_tolerance_of_oracle(name):
   assert frac_1e5 > (0.97 if big else 0.98)
   vel_rel = rel_err(out[..., 3:], ref[..., 3:]).max((1, 2))
   assert (vel_rel < 1e-3).mean() > (0.97 if big else 0.99)
+  # EVERY world above the 1e-4 bar must be explained.  The diagnostic counters (contacts, manifold points, TOI events,
+  # position iterations) do not see every discrete decision (limit engaging, block-solver case, clip-point identity), so
+  # the classification asks the oracle itself: nudge the world's inputs by one fp32 ulp and see how far the ORACLE's own
+  # result moves (common.oracle_sensitivity).  A world may miss the bar only if it is bistable at the one-ulp level -- the
+  # oracle's own spread must then be of the size of the miss (measured on a B200: equal to it to 2-3 digits, i.e. the
+  # CUDA path simply landed on the other branch).  No world may be further from the oracle than the oracle is from itself.
+  bad = np.nonzero(rel > 1e-4)[0]
+  flipped = (v.counters() != ow.counters()).any(1)
+  if len(bad):
+    spread = oracle_sensitivity(env, bodies[bad], None if variants is None else variants[bad], act[bad])
+    for w, s in zip(bad, spread):
+      print(f'  world {w}: rel err {rel[w]:.2e}, counters {"differ" if flipped[w] else "equal"}, oracle moves {s:.2e} under one-ulp input nudges')
+    assert (spread >= 1e-5).all(), 'a world above the bar whose oracle result is insensitive to one-ulp nudges: unexplained'
+    assert (rel[bad] <= 1e-4 + 3.0 * spread).all(), 'further from the oracle than the oracle is from itself'
+  print(f'{name}: {len(bad)} of {n} worlds above 1e-4 rel, all bistable at one ulp; {int(flipped.sum())} worlds with different diagnostic counters')
 
 
 @pytest.mark.parametrize('name', ['Urchin', 'Bounce2', 'LuxoCube', 'CrabCube'])

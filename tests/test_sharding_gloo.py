@@ -24,7 +24,8 @@ def _worker(rank, world, port, n_total, T, out_path):
   hs = HostSim(env.layout.spec, hi - lo, seed=4, world_offset=lo)
   hs.reset()
   r = hs.rollout(T)
-  data = gather_shards({'full_state': r['full_state'], 'lcd_bits': r['lcd_bits'], 'action': r['action']}, rank, world)
+  # small chunks: every array crosses in several point-to-point messages
+  data = gather_shards({'full_state': r['full_state'], 'lcd_bits': r['lcd_bits'], 'action': r['action']}, rank, world, n_total, chunk_bytes=700)
   if rank == 0:
     np.savez(out_path, **data)
   dist.barrier()
@@ -56,3 +57,17 @@ def test_shard_ranges_partition_exactly():
       assert spans[0][0] == 0 and spans[-1][1] == n
       assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
       assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def test_split_is_part_of_the_stream_key():
+  """with one seed, test barrels must not re-create the first train barrels (the reference's are independent draws)"""
+  from boxlcd_b200.collect import split_seed
+  assert split_seed(0, 'train') == 0 and split_seed(5, None) == 5
+  assert split_seed(0, 'test') != split_seed(0, 'train') and split_seed(0, 'test') == split_seed(0, 'test')
+  assert split_seed(0, 'test') != split_seed(1, 'test') and 0 <= split_seed(3, 'val') < 2 ** 64
+  import boxlcd_b200 as blcd
+  from hostsim_py import HostSim
+  env = blcd.envs.Urchin()
+  a = HostSim(env.layout.spec, 4, seed=split_seed(0, 'train')); a.reset()
+  b = HostSim(env.layout.spec, 4, seed=split_seed(0, 'test')); b.reset()
+  assert not (a.rollout(3)['action'] == b.rollout(3)['action']).any()
