@@ -207,11 +207,10 @@ class VecWorldEnv:
     w = width or self.W
     # byte k of a little-endian row word holds pixels 8k .. 8k+7: unpack on uint8 views, so the only intermediate is one
     # byte per pixel (an int32 shift-and-mask would need 4-8 bytes per pixel: tens of GB for a dataset-sized batch)
-    words = 1 if w <= 32 else bits.shape[-1]
-    lead = bits.shape[:-1] if w <= 32 else bits.shape[:-2]
-    by = bits.contiguous().view(torch.uint8).reshape(lead + (4 * words,))
+    rows = bits.shape if w <= 32 else bits.shape[:-1]                  # [..., H]
+    by = bits.contiguous().view(torch.uint8).reshape(rows + (-1,))     # [..., H, 4 * words]
     shifts = torch.arange(8, device=bits.device, dtype=torch.uint8)
-    px = ((by.unsqueeze(-1) >> shifts) & 1).reshape(lead + (32 * words,))
+    px = ((by.unsqueeze(-1) >> shifts) & 1).reshape(rows + (-1,))      # [..., H, 32 * words]
     return px[..., :w].to(torch.bool)
 
   def _obs_numpy(self, obs):

@@ -27,7 +27,7 @@ def random_bodies(env, n, rng, speed=3.0):
   return b.astype(np.float32), variants
 
 
-def oracle_sensitivity(env, bodies, variants, act, copies=48, seed=1):
+def oracle_sensitivity(env, bodies, variants, act, copies=48, seed=1, max_nudges=4, max_ulps=1):
   """How far the ORACLE's own single-step result moves when the inputs of a world are nudged by one fp32 ulp: for every
   world [m] run `copies` oracle copies whose initial state differs from the original in 1-4 randomly chosen components by
   one ulp, and return the largest relative deviation (position / angle) of any copy from the unnudged oracle.  Ordinary
@@ -43,10 +43,12 @@ def oracle_sensitivity(env, bodies, variants, act, copies=48, seed=1):
   for i in range(len(b2)):
     if i % copies == 0:
       continue
-    for _ in range(rng.randint(1, 5)):
+    for _ in range(rng.randint(1, max_nudges + 1)):
       b, k = rng.randint(sp.n_bodies), rng.randint(6)
-      v = b2[i, b, k]
-      b2[i, b, k] = np.nextafter(v, np.float32(v + (1 if rng.rand() < .5 else -1)), dtype=np.float32)
+      up = rng.rand() < .5
+      for _ in range(rng.randint(1, max_ulps + 1)):
+        v = b2[i, b, k]
+        b2[i, b, k] = np.nextafter(v, np.float32(v + (1 if up else -1)), dtype=np.float32)
   ow = oracle.OracleWorlds(sp, len(b2), threads=os.cpu_count() or 1)
   ow.set_bodies(b2, None if variants is None else np.repeat(variants, copies))
   ow.step(np.repeat(act, copies, 0))

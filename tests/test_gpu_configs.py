@@ -159,8 +159,8 @@ def test_errors_are_loud():
     v.render(2048, 32)
   with pytest.raises(IndexError):
     blcd.envs.Dropbox({'walls': 0})     # the reference indexes robots[0] for the scroll offset (world_env.py:382)
-  with pytest.raises(NotImplementedError):
-    blcd.envs.Urchin().lcd_render(lcd_mode='RGB')
+  with pytest.raises(AssertionError, match='lcd_mode'):
+    blcd.envs.Urchin().lcd_render(lcd_mode='L')      # world_env.py:465: only '1' and 'RGB'
 
 
 def test_object2_random_shapes_render_and_step():
