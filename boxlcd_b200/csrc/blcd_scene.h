@@ -71,6 +71,10 @@ struct DScene {
   int32_t off_misc, off_joint, off_clist, clist_words, off_slots, off_cnt, state_words;
   // per-thread shared-memory layout (words), see blcd_world.cuh
   int32_t h_vel, h_pos, h_mass, h_joint, h_con, hot_words;
+  // phase pipeline (blcd_pipeline.cuh): per-world scratch in HBM, word i of world w at scratch[i * n_worlds + w]:
+  // body rows (v, c/a, inverse masses of the nb dynamic rows), joint records, solve bookkeeping (counts, joint order,
+  // islands), pre-solve poses for the TOI sweeps, contact records
+  int32_t x_rows, x_jr, x_misc, x_c0, x_cr, scratch_words;
   DShape wall[BLCD_MAX_WALLS];
   Box wallFat[BLCD_MAX_WALLS];
   V2 wall_n[BLCD_MAX_WALLS];      // unit normal of the wall's line and its offset (n . x = d), for the TOI pre-filter
@@ -324,6 +328,12 @@ inline const char* build_scene(DScene& sc, const blcd_spec& sp, int maxm) {
   sc.h_joint = 0;   // joint and contact records are thread-local (blcd_world.cuh), not in shared memory
   sc.h_con = 0;
   sc.hot_words = sc.h_mass + 2 * (sc.nb + 1);
+  sc.x_rows = 0;
+  sc.x_jr = sc.x_rows + 8 * sc.nb;
+  sc.x_misc = sc.x_jr + kHotJoint * sc.nj;
+  sc.x_c0 = sc.x_misc + 2 + 2 * ((sc.nj + 3) / 4) + (sc.nb + 3) / 4;
+  sc.x_cr = sc.x_c0 + 3 * sc.nb;
+  sc.scratch_words = sc.x_cr + kHotCon * sc.maxm;
   return nullptr;
 }
 

@@ -141,9 +141,12 @@ struct Sim {
   BLCD_HD uint32_t cru(int i) const { return reinterpret_cast<const uint32_t*>(cr)[i]; }
   BLCD_HD uint32_t& jru(int i) { return reinterpret_cast<uint32_t*>(jr)[i]; }
   BLCD_HD uint32_t jru(int i) const { return reinterpret_cast<const uint32_t*>(jr)[i]; }
-  // islands (rebuilt every sub-step)
+  // islands and solve order (rebuilt every sub-step by solve_setup)
   int8_t islandOf[kMaxBodies];
   int nIslands, nc, njo;
+  uint8_t jorder[kMaxJoints];   // joints in b2Island order
+  uint8_t jisl[kMaxJoints];     // island of the k-th joint in solve order
+  uint32_t islDone;             // islands whose position iterations converged (solve_position)
 
   // shared-memory row offsets and the static row index, copied out of the scene table once: the table itself sits in
   // shared memory, where every store to a hot row would force the compiler to re-read it
@@ -169,7 +172,10 @@ struct Sim {
 #endif
     g.p = state + world;
     g.n = n_worlds;
+    x.p = nullptr;
+    x.n = n_worlds;
   }
+  BLCD_HD void attach_scratch(uint32_t* scratch, int64_t world) { x.p = scratch + world; }
 
 #if defined(BLCD_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
   // diagnostic build: cycles per phase, accumulated into the counter words (which then no longer hold the usual counts)
@@ -208,6 +214,97 @@ struct Sim {
     ph(5);                // (diagnostic build) time spent waiting at the barrier
 #endif
 #endif
+  }
+
+  // ---- phase pipeline: spill / fill of what lives between the phases of one sub-step (blcd_pipeline.cuh) -------------
+  Gw x;   // this world's scratch words in HBM
+  BLCD_HD void x_rows_out(int first, int words) const {   // body rows: [v 3][c a 3][invMass invI 2] x nb, dynamic rows only
+    const int nb = sc.nb;
+    for (int b = 0; b < nb; ++b)
+      for (int k = first; k < first + words; ++k)
+        x.f(sc.x_rows + 8 * b + k) = k < 3 ? hot[oV + 3 * b + k] : (k < 6 ? hot[oP + 3 * b + k - 3] : hot[oM + 2 * b + k - 6]);
+  }
+  BLCD_HD void x_rows_in(int first, int words) const {
+    const int nb = sc.nb;
+    for (int b = 0; b < nb; ++b)
+      for (int k = first; k < first + words; ++k) {
+        float val = x.f(sc.x_rows + 8 * b + k);
+        if (k < 3) hot[oV + 3 * b + k] = val; else if (k < 6) hot[oP + 3 * b + k - 3] = val; else hot[oM + 2 * b + k - 6] = val;
+      }
+    // the static row that stands in for every wall
+    set_hv(nb, mk(0.0f, 0.0f), 0.0f);
+    set_hc(nb, mk(0.0f, 0.0f), 0.0f);
+    hot[oM + 2 * nb] = 0.0f;
+    hot[oM + 2 * nb + 1] = 0.0f;
+  }
+  BLCD_HD void x_misc_out() const {
+    x.u(sc.x_misc) = (uint32_t)nc | ((uint32_t)njo << 8) | ((uint32_t)nIslands << 16);
+    x.u(sc.x_misc + 1) = islDone;
+    const int jw = (sc.nj + 3) / 4, bw = (sc.nb + 3) / 4;
+    for (int i = 0; i < jw; ++i) {
+      uint32_t a_ = 0u, b_ = 0u;
+      for (int k = 0; k < 4; ++k) {
+        int j = 4 * i + k;
+        if (j < njo) { a_ |= (uint32_t)jorder[j] << (8 * k); b_ |= (uint32_t)jisl[j] << (8 * k); }
+      }
+      x.u(sc.x_misc + 2 + i) = a_;
+      x.u(sc.x_misc + 2 + jw + i) = b_;
+    }
+    for (int i = 0; i < bw; ++i) {
+      uint32_t a_ = 0u;
+      for (int k = 0; k < 4; ++k) {
+        int b = 4 * i + k;
+        if (b < sc.nb) a_ |= (uint32_t)(uint8_t)islandOf[b] << (8 * k);
+      }
+      x.u(sc.x_misc + 2 + 2 * jw + i) = a_;
+    }
+  }
+  BLCD_HD void x_misc_in() {
+    uint32_t w0 = x.u(sc.x_misc);
+    nc = (int)(w0 & 255u); njo = (int)((w0 >> 8) & 255u); nIslands = (int)(w0 >> 16);
+    islDone = x.u(sc.x_misc + 1);
+    const int jw = (sc.nj + 3) / 4, bw = (sc.nb + 3) / 4;
+    for (int i = 0; i < jw; ++i) {
+      uint32_t a_ = x.u(sc.x_misc + 2 + i), b_ = x.u(sc.x_misc + 2 + jw + i);
+      for (int k = 0; k < 4; ++k) {
+        int j = 4 * i + k;
+        if (j < kMaxJoints) { jorder[j] = (uint8_t)(a_ >> (8 * k)); jisl[j] = (uint8_t)(b_ >> (8 * k)); }
+      }
+    }
+    for (int i = 0; i < bw; ++i) {
+      uint32_t a_ = x.u(sc.x_misc + 2 + 2 * jw + i);
+      for (int k = 0; k < 4; ++k) {
+        int b = 4 * i + k;
+        if (b < kMaxBodies) islandOf[b] = (int8_t)(uint8_t)(a_ >> (8 * k));
+      }
+    }
+  }
+  BLCD_HD void x_jr_out(int first, int words) const {
+    for (int j = 0; j < sc.nj; ++j)
+      for (int k = first; k < first + words; ++k) x.u(sc.x_jr + kHotJoint * j + k) = jru(kHotJoint * j + k);
+  }
+  BLCD_HD void x_jr_in(int first, int words) {
+    for (int j = 0; j < sc.nj; ++j)
+      for (int k = first; k < first + words; ++k) jru(kHotJoint * j + k) = x.u(sc.x_jr + kHotJoint * j + k);
+  }
+  // contact records: the header and as many point records as the solver uses (1 when the block solver was refused)
+  BLCD_HD void x_cr_out() const {
+    for (int k = 0; k < nc; ++k) {
+      const int pts = (int)((cru(kHotCon * k + C_PK) >> 10) & 3u);
+      const int words = kHotConHdr + kHotConPt * (pts < 1 ? 1 : pts);
+      for (int i = 0; i < words; ++i) x.u(sc.x_cr + kHotCon * k + i) = cru(kHotCon * k + i);
+    }
+  }
+  BLCD_HD void x_cr_in() {
+    for (int k = 0; k < nc; ++k) {
+      const uint32_t pk = x.u(sc.x_cr + kHotCon * k + C_PK);
+      const int pts = (int)((pk >> 10) & 3u);
+      const int words = kHotConHdr + kHotConPt * (pts < 1 ? 1 : pts);
+      for (int i = 0; i < words; ++i) cru(kHotCon * k + i) = x.u(sc.x_cr + kHotCon * k + i);
+    }
+  }
+  BLCD_HD void x_cr_pk_in() {   // position iterations only need the packed word (rows, slot, island)
+    for (int k = 0; k < nc; ++k) cru(kHotCon * k + C_PK) = x.u(sc.x_cr + kHotCon * k + C_PK);
   }
 
   // ---- scene helpers ------------------------------------------------------------------------------------------------
@@ -273,6 +370,10 @@ struct Sim {
     }
     for (int k = 0; k < BLCD_N_COUNTERS; ++k) cnt[k] = g.u(sc.off_cnt + k);
     moved = 0u;
+  }
+
+  BLCD_HD void load_variant() {   // shape variants only (pipeline phases that need local centres / radii but no body state)
+    variant = kVariantInFlags ? ((g.u(sc.off_misc + 0) >> kVariantShift) & kBodyMask) : g.u(sc.off_misc + 4);
   }
 
   BLCD_HD void store() {
@@ -1094,15 +1195,26 @@ struct Sim {
   }
 
   // ---- b2World::Solve -------------------------------------------------------------------------------------------------
+  // Split into the five phases a sub-step's solve consists of.  The fused kernels (k_step / k_rollout) run them back to
+  // back from one thread; the phase pipeline (blcd_pipeline.cuh) runs each as its own kernel with the records in between
+  // spilled to a per-world scratch area in HBM -- same functions, same order, same results.
   BLCD_HD void solve(float h_dt, float dtRatio) {
+    solve_setup(h_dt, dtRatio);
+    if (sc.align_mode >= 1) phase_align(0); else reconverge();   // end of: narrow phase, islands, constraint setup
+    solve_velocity(h_dt);
+    solve_integrate(h_dt);
+    if (sc.align_mode >= 2) phase_align(1); else reconverge();   // end of: velocity iterations
+    solve_position();
+    if (sc.align_mode >= 4) phase_align(2); else reconverge();   // end of: position iterations
+    solve_finish(h_dt);
+  }
+
+  // islands (Box2D's DFS order), velocity integration, contact / joint velocity-constraint records, warm starting
+  BLCD_HD void solve_setup(float h_dt, float dtRatio) {
     const int nb = sc.nb;
-    uint8_t corder[32];           // contact record k -> nothing to map: records are filled in solve order
-    uint8_t jorder[kMaxJoints];
-    uint8_t jisl[kMaxJoints];
     uint8_t stack[kMaxBodies];
     PairMask cflag = PairMask::none();
     uint32_t jflag = 0u;
-    (void)corder;
     for (int b = 0; b < kMaxBodies; ++b) islandOf[b] = -1;
     nIslands = 0; nc = 0; njo = 0;
     stage_rows();
@@ -1176,8 +1288,11 @@ struct Sim {
     }
     for (int k = 0; k < nc; ++k) contact_warm_start(k);
     for (int k = 0; k < njo; ++k) joint_init(jorder[k], jisl[k], dtRatio, h_dt);
+  }
+
+  // b2Island::Solve's velocity iterations + b2ContactSolver::StoreImpulses
+  BLCD_HD void solve_velocity(float h_dt) {
     const int vi = sc.vel_iters;
-    if (sc.align_mode >= 1) phase_align(0); else reconverge();   // end of: narrow phase, islands, constraint setup
     if (njo <= 3) {
       // up to three joints (every reference robot in scope) live in registers for the whole loop; contacts, whose
       // number is data dependent, stay in shared memory
@@ -1205,7 +1320,11 @@ struct Sim {
       }
     }
     for (int k = 0; k < nc; ++k) contact_store_impulses(k);
-    // integrate positions
+  }
+
+  // b2Island::Solve: integrate positions (maxTranslation / maxRotation clamps)
+  BLCD_HD void solve_integrate(float h_dt) {
+    const int nb = sc.nb;
     for (int b = 0; b < nb; ++b) {
       if (islandOf[b] < 0) continue;
       V2 cc = hc(b), vv = hv(b);
@@ -1219,9 +1338,11 @@ struct Sim {
       set_hc(b, cc, aa);
       set_hv(b, vv, ww);
     }
-    // position iterations; every island stops on its own convergence
-    if (sc.align_mode >= 2) phase_align(1); else reconverge();   // end of: velocity iterations
-    uint32_t islDone = 0u;
+  }
+
+  // position iterations; every island stops on its own convergence
+  BLCD_HD void solve_position() {
+    islDone = 0u;
     const uint32_t islAll = (1u << nIslands) - 1u;
     for (int it = 0; it < sc.pos_iters && islDone != islAll; ++it) {
       uint32_t bad = 0u;
@@ -1239,8 +1360,11 @@ struct Sim {
       }
       islDone |= ~bad & islAll;
     }
-    // write back + SynchronizeTransform
-    if (sc.align_mode >= 4) phase_align(2); else reconverge();   // end of: position iterations
+  }
+
+  // write back + SynchronizeTransform, sleeping, broad phase
+  BLCD_HD void solve_finish(float h_dt) {
+    const int nb = sc.nb;
     Xf xf1[kMaxBodies];
     for (int b = 0; b < nb; ++b) {
       if (islandOf[b] < 0) continue;
@@ -1517,26 +1641,34 @@ struct Sim {
   BLCD_HD void b2_step() {
     const float dt = sc.dt;
     if (sc.align_mode >= 3) phase_align(4); else reconverge();   // end of: TOI of the previous sub-step (+ observation)
+    substep_collide();
+    solve(dt, inv_dt0 * dt);
+    if (sc.align_mode >= 3) phase_align(3); else reconverge();   // end of: write-back, sleep, broad phase
+    if (!(sc.flags & BLCD_FLAG_NO_TOI)) solve_toi(dt);
+    reconverge();
+    substep_end();
+  }
+
+  // b2World::Step up to b2World::Solve: pending FindNewContacts, then b2ContactManager::Collide
+  BLCD_HD void substep_collide() {
     if (newFixture) {
       find_new_contacts((1u << (sc.nw + sc.nb)) - 1u);
       newFixture = false;
     }
-    float dtRatio = inv_dt0 * dt;
     collide();
-    solve(dt, dtRatio);
-    if (sc.align_mode >= 3) phase_align(3); else reconverge();   // end of: write-back, sleep, broad phase
-    if (!(sc.flags & BLCD_FLAG_NO_TOI)) solve_toi(dt);
-    reconverge();
-    inv_dt0 = 1.0f / dt;
+  }
+
+  // end of b2World::Step: m_inv_dt0, plus this library's diagnostic counters
+  BLCD_HD void substep_end() {
+    inv_dt0 = 1.0f / sc.dt;
     ++cnt[BLCD_CNT_SUBSTEPS];
     for (int s = 0; s < sc.maxm; ++s)
       if ((slotUsed >> s) & 1u) cnt[BLCD_CNT_MANIFOLD_POINTS] += (g.u(slot_base(s) + S_HDR) >> 16) & 0xFFu;
     cnt[BLCD_CNT_SLEEP_STEPS] += (uint32_t)(sc.nb - popc(awake & ((1u << sc.nb) - 1u)));
   }
 
-  // WorldEnv.step (world_env.py:431-452): motor speeds from the clipped action, then n_substeps world steps
-  BLCD_HD void env_step(const float* action) {
-    if (sc.align_mode >= 5) phase_align(4);
+  // WorldEnv.step (world_env.py:431-445): motor speeds from the clipped action (SetMotorSpeed wakes both bodies)
+  BLCD_HD void env_step_begin(const float* action) {
     ep_t += 1;
     for (int j = 0; j < sc.nj; ++j) {
       const DJoint& jd = sc.joint[j];
@@ -1547,7 +1679,48 @@ struct Sim {
       set_awake(jd.b);
       jr[kHotJoint * j + J_MS] = (float)(jd.speed * av);
     }
+  }
+
+  // WorldEnv.step (world_env.py:431-452): motor speeds from the clipped action, then n_substeps world steps
+  BLCD_HD void env_step(const float* action) {
+    if (sc.align_mode >= 5) phase_align(4);
+    env_step_begin(action);
     for (int s = 0; s < sc.nsub; ++s) b2_step();
+  }
+
+  // Would b2World::SolveTOI do anything for this world?  Its first scan visits, in contact-list order, every candidate pair
+  // of an awake body with a wall, counts it, and queries the time of impact unless the pre-filter already knows the answer
+  // (alpha = 1).  If every pair is pre-filtered the scan finds no event and SolveTOI changes nothing but that counter, so
+  // the pipeline finishes the sub-step right away and only worlds with a real query go on to the TOI kernel.
+  // Call with c0 / a0 = the pre-solve pose and c / a / xf = the solved one.  Returns true if a query is needed; otherwise
+  // the counter has been advanced exactly as SolveTOI would have.
+  BLCD_HD bool toi_needed() {
+    const int nw = sc.nw;
+    int eligible = 0;
+    uint32_t bodies = 0u;    // awake bodies with a wall pair in the list
+    PairMask seen = PairMask::none();
+    for (int k = 0; k < ncl; ++k) {
+      int p = clist[k];
+      int fa = sc.pair[p].fa, fb = sc.pair[p].fb;
+      if (fa >= nw) continue;
+      int b = fb - nw;
+      if (!is_awake(b)) continue;
+      ++eligible;
+      bodies |= 1u << b;
+      seen.set(p);
+    }
+    bool need = false;
+    for (int b = 0; b < kMaxBodies; ++b) {
+      if (b < sc.nb && ((bodies >> b) & 1u)) {
+        uint32_t m = toi_prefilter(b);
+        for (int k = 0; k < ncl; ++k) {
+          int p = clist[k];
+          if (seen.test(p) && sc.pair[p].fb - nw == b && ((m >> sc.pair[p].fa) & 1u)) need = true;
+        }
+      }
+    }
+    if (!need) cnt[BLCD_CNT_TOI_CALLS] += (uint32_t)eligible;
+    return need;
   }
 
   BLCD_HD void draw_action(float* action) {

@@ -15,7 +15,7 @@
 #include <type_traits>
 #include <utility>
 #include <vector>
-#include "blcd_world.cuh"
+#include "blcd_pipeline.cuh"
 
 // This file is compiled once per scene-size profile (blcd_profile.h).  Its C entry points carry the profile's prefix
 // (blcd_small_* / blcd_large_*, declared in blcd_profile_api.h); blcd_dispatch.cpp owns the public blcd_* symbols.
@@ -245,14 +245,96 @@ __global__ void __launch_bounds__(BLOCK, BLOCK >= 256 ? 1 : 256 / BLOCK) k_rollo
 }
 
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_observe(const DScene* scene_g, uint32_t* state, int64_t n, OutPtrs out) {
+__global__ void __launch_bounds__(BLOCK) k_observe(const DScene* scene_g, uint32_t* state, int64_t n, OutPtrs out, int64_t w_begin, int64_t w_end) {
   unsigned char* smem_raw = blcd_smem;
   const DScene& sc = stage_scene<BLOCK>(scene_g, smem_raw);
-  int64_t w = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-  if (w >= n) return;
+  int64_t w = w_begin + (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (w >= w_end) return;
   Sim<BLOCK> sim(sc, hot_base<BLOCK>(smem_raw), state, n, w);
   sim.load(0, 0);
   write_obs<BLOCK>(sim, sc, out, w);
+}
+
+// ---- phase pipeline kernels (blcd_pipeline.cuh): one sub-step = pre -> vel -> pos -> post -> toi over worlds [w_begin, w_end) --
+// All of them: one thread per world, kPipeBlock threads per block (body rows in shared memory [word][thread]), no
+// block-level synchronisation after the scene table is staged, so blocks and warps drift freely.
+constexpr int kPipeBlock = 128;
+// resident blocks per SM each phase kernel is compiled for (register cap = 65536 / (128 x blocks)) and given shared memory for
+constexpr int kPreBlocks = 4, kVelBlocks = 4, kPosBlocks = 6, kPostBlocks = 5, kToiBlocks = 3;
+
+// mode 0: blcd_step (actions given or drawn; out.actions [N, A]); mode 1: blcd_rollout (obs_t and a_t recorded at row w T + t)
+__global__ void __launch_bounds__(kPipeBlock, kPreBlocks) k_pipe_pre(const DScene* scene_g, uint32_t* state, uint32_t* scratch, int64_t n, uint64_t seed, int64_t world_offset,
+                                                            const float* actions, int mode, int T, int t, int first, OutPtrs out,
+                                                            int64_t w_begin, int64_t w_end, uint32_t* toi_count) {
+  unsigned char* smem_raw = blcd_smem;
+  const DScene& sc = stage_scene<kPipeBlock>(scene_g, smem_raw);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *toi_count = 0u;   // the list of this sub-step's TOI worlds starts empty
+  int64_t w = w_begin + (int64_t)blockIdx.x * kPipeBlock + threadIdx.x;
+  if (w >= w_end) return;
+  Sim<kPipeBlock> sim(sc, hot_base<kPipeBlock>(smem_raw), state, n, w, w_end);
+  sim.attach_scratch(scratch, w);
+  sim.load(seed, world_offset + w);
+  float act[kMaxObs];
+  if (first) {
+    if (mode == 1) {
+      int64_t row = w * T + t;
+      write_obs<kPipeBlock>(sim, sc, out, row);   // obs_t is recorded before action t (collect.py:33-39)
+      sim.draw_action(act);
+      if (out.actions)
+        for (int k = 0; k < sc.A; ++k) __stcs(out.actions + row * sc.A + k, act[k]);
+    } else {
+      if (actions) { for (int k = 0; k < sc.A; ++k) act[k] = actions[w * sc.A + k]; }
+      else sim.draw_action(act);
+      if (out.actions)
+        for (int k = 0; k < sc.A; ++k) out.actions[w * sc.A + k] = act[k];
+    }
+  }
+  pipe_pre(sim, first != 0, act);
+}
+
+__global__ void __launch_bounds__(kPipeBlock, kVelBlocks) k_pipe_vel(const DScene* scene_g, uint32_t* state, uint32_t* scratch, int64_t n, int64_t w_begin, int64_t w_end) {
+  unsigned char* smem_raw = blcd_smem;
+  const DScene& sc = stage_scene<kPipeBlock>(scene_g, smem_raw);
+  int64_t w = w_begin + (int64_t)blockIdx.x * kPipeBlock + threadIdx.x;
+  if (w >= w_end) return;
+  Sim<kPipeBlock> sim(sc, hot_base<kPipeBlock>(smem_raw), state, n, w, w_end);
+  sim.attach_scratch(scratch, w);
+  pipe_vel(sim);
+}
+
+__global__ void __launch_bounds__(kPipeBlock, kPosBlocks) k_pipe_pos(const DScene* scene_g, uint32_t* state, uint32_t* scratch, int64_t n, int64_t w_begin, int64_t w_end) {
+  unsigned char* smem_raw = blcd_smem;
+  const DScene& sc = stage_scene<kPipeBlock>(scene_g, smem_raw);
+  int64_t w = w_begin + (int64_t)blockIdx.x * kPipeBlock + threadIdx.x;
+  if (w >= w_end) return;
+  Sim<kPipeBlock> sim(sc, hot_base<kPipeBlock>(smem_raw), state, n, w, w_end);
+  sim.attach_scratch(scratch, w);
+  pipe_pos(sim);
+}
+
+__global__ void __launch_bounds__(kPipeBlock, kPostBlocks) k_pipe_post(const DScene* scene_g, uint32_t* state, uint32_t* scratch, int64_t n, uint64_t seed, int64_t world_offset,
+                                                             int64_t w_begin, int64_t w_end, uint32_t* toi_count, uint32_t* toi_list) {
+  unsigned char* smem_raw = blcd_smem;
+  const DScene& sc = stage_scene<kPipeBlock>(scene_g, smem_raw);
+  int64_t w = w_begin + (int64_t)blockIdx.x * kPipeBlock + threadIdx.x;
+  if (w >= w_end) return;
+  Sim<kPipeBlock> sim(sc, hot_base<kPipeBlock>(smem_raw), state, n, w, w_end);
+  sim.attach_scratch(scratch, w);
+  sim.load(seed, world_offset + w);
+  if (pipe_post(sim)) toi_list[atomicAdd(toi_count, 1u)] = (uint32_t)(w - w_begin);
+}
+
+__global__ void __launch_bounds__(kPipeBlock, kToiBlocks) k_pipe_toi(const DScene* scene_g, uint32_t* state, uint32_t* scratch, int64_t n, uint64_t seed, int64_t world_offset,
+                                                            int64_t w_begin, const uint32_t* toi_count, const uint32_t* toi_list) {
+  unsigned char* smem_raw = blcd_smem;
+  const DScene& sc = stage_scene<kPipeBlock>(scene_g, smem_raw);
+  int64_t i = (int64_t)blockIdx.x * kPipeBlock + threadIdx.x;
+  if (i >= (int64_t)*toi_count) return;
+  int64_t w = w_begin + (int64_t)toi_list[i];
+  Sim<kPipeBlock> sim(sc, hot_base<kPipeBlock>(smem_raw), state, n, w);
+  sim.attach_scratch(scratch, w);
+  sim.load(seed, world_offset + w);
+  pipe_toi(sim);
 }
 
 // lcd_render from poses.  One thread per (frame, row): lanes 0..H-1 of consecutive frames write consecutive words, so the
@@ -372,6 +454,11 @@ struct BLCD_PENV {
   cudaEvent_t hev[kHostDepth][kHostStreams] = {};       // completion of host step s (ring) on each stream
   uint64_t host_submitted = 0, host_completed = 0;
   int host_chunks = 0, host_chunks_env = -1;
+  // phase pipeline (blcd_pipeline.cuh)
+  int pipeline = 0;                 // 1: blcd_step / blcd_rollout run the phase pipeline instead of the fused kernel
+  uint32_t* scratch = nullptr;      // [scratch_words][n]
+  uint32_t* toi_count = nullptr;    // [kHostStreams] one counter per concurrently processed world range
+  uint32_t* toi_list = nullptr;     // [n] range-relative world indices that need SolveTOI in the current sub-step
 };
 
 namespace {
@@ -397,10 +484,11 @@ int launch_sized(BLCD_PENV* h, F f) {
 }
 
 template <typename K>
-int set_smem_attr(K kernel, size_t bytes) {
+int set_smem_attr(K kernel, size_t bytes, int blocks_per_sm = 1) {
   CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  // the rest of the 256 KB on-chip array serves as L1 for the thread-local constraint records
-  int pct = (int)((bytes + 1024) * 100 / (228 * 1024)) + 1;
+  // shared memory for `blocks_per_sm` resident blocks; the rest of the 256 KB on-chip array serves as L1 for the
+  // thread-local constraint records
+  int pct = (int)((bytes + 1024) * blocks_per_sm * 100 / (228 * 1024)) + 1;
   CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct));
   return 0;
 }
@@ -465,6 +553,7 @@ int BLCD_P(create)(const blcd_spec* spec_host, int64_t n_worlds, int device, uin
     }
   }
   if (const char* e = getenv("BLCD_BLOCK")) h->block = atoi(e);
+  if (const char* e = getenv("BLCD_PIPELINE")) h->pipeline = atoi(e) != 0;
   {
 #if BLCD_PROFILE_ID == 0
     const int sizes[] = {512, 448, 384, 320, 256, 128, 64};
@@ -540,6 +629,7 @@ int BLCD_P(destroy)(BLCD_PENV* h) {
   if (h->h_bits) cudaFreeHost(h->h_bits);
   if (h->h_done) cudaFreeHost(h->h_done);
   cudaFree(h->d_act); cudaFree(h->d_fs); cudaFree(h->d_bits); cudaFree(h->d_done);
+  cudaFree(h->scratch); cudaFree(h->toi_count); cudaFree(h->toi_list);
   for (auto& r : h->pinned_user) cudaHostUnregister(const_cast<void*>(r.first));
   for (auto& ring : h->hev) for (auto& e : ring) if (e) cudaEventDestroy(e);
   delete h;
@@ -615,7 +705,64 @@ int BLCD_P(get_poses)(BLCD_PENV* h, float* poses_dev, uint32_t* variant_dev, uin
   return 0;
 }
 
-static int step_range(BLCD_PENV* h, const float* actions_dev, int n_steps, OutPtrs out, cudaStream_t st, int64_t w_begin, int64_t w_end) {
+// ---- phase pipeline: host side ---------------------------------------------------------------------------------------
+static int pipeline_prepare(BLCD_PENV* h) {
+  if (h->scratch) return 0;
+  CK(cudaMalloc(&h->scratch, (size_t)h->scene.scratch_words * (size_t)h->n * 4));
+  CK(cudaMalloc(&h->toi_count, kHostStreams * sizeof(uint32_t)));
+  CK(cudaMemset(h->toi_count, 0, kHostStreams * sizeof(uint32_t)));
+  CK(cudaMalloc(&h->toi_list, (size_t)h->n * sizeof(uint32_t)));
+  const size_t sb = smem_bytes(h, kPipeBlock);
+  if (set_smem_attr(k_pipe_pre, sb, kPreBlocks) || set_smem_attr(k_pipe_vel, sb, kVelBlocks) || set_smem_attr(k_pipe_pos, sb, kPosBlocks) ||
+      set_smem_attr(k_pipe_post, sb, kPostBlocks) || set_smem_attr(k_pipe_toi, sb, kToiBlocks))
+    return -1;
+  return 0;
+}
+
+// T env steps of worlds [w0, w1) on stream st: per sub-step five launches.  mode 0: blcd_step semantics (actions_dev or the
+// device RNG, T == 1); mode 1: blcd_rollout semantics (obs_t / a_t recorded before step t).  `slot`: which TOI counter to
+// use (ranges running concurrently on different streams need their own).
+static int pipeline_run(BLCD_PENV* h, const float* actions_dev, int mode, int T, OutPtrs out, cudaStream_t st, int64_t w0, int64_t w1, int slot) {
+  if (pipeline_prepare(h)) return -1;
+  if (w1 <= w0) return 0;
+  const unsigned blocks = (unsigned)((w1 - w0 + kPipeBlock - 1) / kPipeBlock);
+  const size_t sb = smem_bytes(h, kPipeBlock);
+  uint32_t* cnt = h->toi_count + slot;
+  uint32_t* list = h->toi_list + w0;
+  for (int t = 0; t < T; ++t) {
+    for (int s = 0; s < h->scene.nsub; ++s) {
+      k_pipe_pre<<<blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, h->seed, h->world_offset, actions_dev, mode, T, t, s == 0 ? 1 : 0, out,
+                                                 w0, w1, cnt);
+      k_pipe_vel<<<blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, w0, w1);
+      k_pipe_pos<<<blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, w0, w1);
+      k_pipe_post<<<blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, h->seed, h->world_offset, w0, w1, cnt, list);
+      k_pipe_toi<<<blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, h->seed, h->world_offset, w0, cnt, list);
+      h->launches += 5;
+    }
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int step_range(BLCD_PENV* h, const float* actions_dev, int n_steps, OutPtrs out, cudaStream_t st, int64_t w_begin, int64_t w_end, int slot = 0) {
+  if (h->pipeline) {
+    OutPtrs o = out;
+    OutPtrs act_only = {nullptr, nullptr, nullptr, nullptr, nullptr, out.actions};
+    for (int i = 0; i < n_steps; ++i)
+      if (pipeline_run(h, actions_dev, 0, 1, act_only, st, w_begin, w_end, slot)) return -1;
+    o.actions = nullptr;
+    if (o.full_state || o.proprio || o.lcd_bits || o.lcd_bool || o.done) {
+      int rc = launch_sized(h, [&](auto B) {
+        constexpr int BLOCK = decltype(B)::value;
+        k_observe<BLOCK><<<(unsigned)((w_end - w_begin + BLOCK - 1) / BLOCK), BLOCK, smem_bytes(h, BLOCK), st>>>(h->scene_dev, h->state, h->n, o, w_begin, w_end);
+        return 0;
+      });
+      if (rc) return rc;
+      CK(cudaGetLastError());
+      h->launches += 1;
+    }
+    return 0;
+  }
   int rc = launch_sized(h, [&](auto B) {
     constexpr int BLOCK = decltype(B)::value;
     k_step<BLOCK><<<(unsigned)((w_end - w_begin + BLOCK - 1) / BLOCK), BLOCK, smem_bytes(h, BLOCK), st>>>(h->scene_dev, h->state, h->n, h->seed, h->world_offset,
@@ -657,7 +804,7 @@ int BLCD_P(observe)(BLCD_PENV* h, float* full_state_dev, float* proprio_dev, uin
   OutPtrs out = {full_state_dev, proprio_dev, lcd_bits_dev, lcd_bool_dev, done_dev, nullptr};
   int rc = launch_sized(h, [&](auto B) {
     constexpr int BLOCK = decltype(B)::value;
-    k_observe<BLOCK><<<(unsigned)((h->n + BLOCK - 1) / BLOCK), BLOCK, smem_bytes(h, BLOCK), st>>>(h->scene_dev, h->state, h->n, out);
+    k_observe<BLOCK><<<(unsigned)((h->n + BLOCK - 1) / BLOCK), BLOCK, smem_bytes(h, BLOCK), st>>>(h->scene_dev, h->state, h->n, out, 0, h->n);
     return 0;
   });
   if (rc) return rc;
@@ -672,6 +819,10 @@ int BLCD_P(rollout)(BLCD_PENV* h, int32_t T, float* full_state_dev, uint32_t* lc
   cudaStream_t st = (cudaStream_t)stream;
   OutPtrs out = {full_state_dev, nullptr, lcd_bits_dev, nullptr, nullptr, actions_dev};
   if (begin_timing(h, st)) return -1;
+  if (h->pipeline) {
+    if (pipeline_run(h, nullptr, 1, T, out, st, 0, h->n, 0)) return -1;
+    return end_timing(h, st);
+  }
   int rc = launch_sized(h, [&](auto B) {
     constexpr int BLOCK = decltype(B)::value;
     k_rollout<BLOCK><<<(unsigned)((h->n + BLOCK - 1) / BLOCK), BLOCK, smem_bytes(h, BLOCK), st>>>(h->scene_dev, h->state, h->n, h->seed, h->world_offset, T, out);
@@ -735,7 +886,7 @@ static int host_step_submit(BLCD_PENV* h, const float* act_src, float* fs_dst, u
       const size_t cnt = (size_t)(w1 - w0);
       if (act_src) CK(cudaMemcpyAsync(h->d_act + w0 * sc.A, act_src + w0 * sc.A, cnt * sc.A * 4, cudaMemcpyHostToDevice, st));
       OutPtrs out = {fs_dst ? h->d_fs : nullptr, nullptr, bits_dst ? h->d_bits : nullptr, nullptr, done_dst ? h->d_done : nullptr, nullptr};
-      if (step_range(h, act_src ? h->d_act : nullptr, 1, out, st, w0, w1)) return -1;
+      if (step_range(h, act_src ? h->d_act : nullptr, 1, out, st, w0, w1, c)) return -1;
       if (fs_dst) CK(cudaMemcpyAsync(fs_dst + w0 * sc.S, h->d_fs + w0 * sc.S, cnt * sc.S * 4, cudaMemcpyDeviceToHost, st));
       if (bits_dst) CK(cudaMemcpyAsync(bits_dst + w0 * sc.lcd_h * lw, h->d_bits + w0 * sc.lcd_h * lw, cnt * sc.lcd_h * lw * 4, cudaMemcpyDeviceToHost, st));
       if (done_dst) CK(cudaMemcpyAsync(done_dst + w0, h->d_done + w0, cnt, cudaMemcpyDeviceToHost, st));

@@ -4,7 +4,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
-#include "blcd_world.cuh"
+#include <new>
+#include "blcd_pipeline.cuh"
 
 using namespace BLCD_NS;
 
@@ -12,6 +13,7 @@ struct HostSim {
   DScene scene;
   std::vector<uint32_t> state;
   std::vector<float> hot;
+  std::vector<uint32_t> scratch;   // phase pipeline: [word][world], like the device buffer
   int64_t n, offset;
   uint64_t seed;
 };
@@ -25,6 +27,7 @@ void* hostsim_new(const blcd_spec* spec, int64_t n, uint64_t seed, int64_t offse
   h->n = n; h->seed = seed; h->offset = offset;
   h->state.assign((size_t)h->scene.state_words * n, 0u);
   h->hot.assign((size_t)h->scene.hot_words, 0.0f);
+  h->scratch.assign((size_t)h->scene.scratch_words * n, 0xDEADBEEFu);
   for (int64_t w = 0; w < n; ++w)
     for (int s = 0; s < h->scene.maxm; ++s) h->state[(size_t)(h->scene.off_slots + kSlotWords * s) * n + w] = kSlotFree;
   return h;
@@ -99,6 +102,64 @@ void hostsim_step(void* p, const float* actions, float* actions_out) {
     if (actions_out) memcpy(actions_out + w * sc.A, act, sizeof(float) * sc.A);
     sim.env_step(act);
     sim.store();
+  }
+}
+
+// ---- the phase pipeline (blcd_pipeline.cuh) on the host: every phase runs in a FRESH, poisoned Sim object, so anything a
+// phase needs must really travel through the state / scratch buffers, exactly as between two kernels on the device -------
+namespace {
+struct Phase {
+  alignas(64) unsigned char buf[sizeof(Sim<1>)];
+  Sim<1>* sim;
+  Phase(HostSim* h, int64_t w, bool load) {
+    memset(buf, 0xAB, sizeof(buf));
+    for (auto& x : h->hot) { uint32_t poison = 0xABABABABu; memcpy(&x, &poison, 4); }
+    sim = new (buf) Sim<1>(h->scene, h->hot.data(), h->state.data(), h->n, w);
+    sim->attach_scratch(h->scratch.data(), w);
+    if (load) sim->load(h->seed, h->offset + w);
+  }
+};
+
+void pipeline_env_step(HostSim* h, int64_t w, const float* act) {
+  for (int s = 0; s < h->scene.nsub; ++s) {
+    { Phase p(h, w, true); pipe_pre(*p.sim, s == 0, act); }
+    { Phase p(h, w, false); pipe_vel(*p.sim); }
+    { Phase p(h, w, false); pipe_pos(*p.sim); }
+    bool need;
+    { Phase p(h, w, true); need = pipe_post(*p.sim); }
+    if (need) { Phase p(h, w, true); pipe_toi(*p.sim); }
+  }
+}
+}  // namespace
+
+void hostsim_step_pipeline(void* p, const float* actions, float* actions_out) {
+  HostSim* h = (HostSim*)p;
+  const DScene& sc = h->scene;
+  for (int64_t w = 0; w < h->n; ++w) {
+    float act[BLCD_MAX_OBS];
+    if (actions) memcpy(act, actions + w * sc.A, sizeof(float) * sc.A);
+    else { SIM(w); sim.draw_action(act); sim.store(); }
+    if (actions_out) memcpy(actions_out + w * sc.A, act, sizeof(float) * sc.A);
+    pipeline_env_step(h, w, act);
+  }
+}
+
+void hostsim_rollout_pipeline(void* p, int T, float* full_state, uint32_t* bits, float* actions) {
+  HostSim* h = (HostSim*)p;
+  const DScene& sc = h->scene;
+  for (int64_t w = 0; w < h->n; ++w) {
+    for (int t = 0; t < T; ++t) {
+      int64_t row = w * T + t;
+      float act[BLCD_MAX_OBS];
+      {
+        SIM(w);
+        write_obs(sim, sc, full_state ? full_state + row * sc.S : nullptr, bits ? bits + row * sc.lcd_h * row_words(sc.lcd_w) : nullptr);
+        sim.draw_action(act);
+        sim.store();
+      }
+      if (actions) memcpy(actions + row * sc.A, act, sizeof(float) * sc.A);
+      pipeline_env_step(h, w, act);
+    }
   }
 }
 

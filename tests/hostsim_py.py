@@ -31,6 +31,8 @@ def lib(large=False):
     l.hostsim_step.argtypes = [vp, vp, vp]
     l.hostsim_observe.argtypes = [vp, vp, vp]
     l.hostsim_rollout.argtypes = [vp, C.c_int, vp, vp, vp]
+    l.hostsim_step_pipeline.argtypes = [vp, vp, vp]
+    l.hostsim_rollout_pipeline.argtypes = [vp, C.c_int, vp, vp, vp]
     l.hostsim_counters.argtypes = [vp, vp]
     l.hostsim_render_poses.argtypes = [vp, vp, vp, i64, C.c_int, C.c_int, vp]
     _libs[path] = l
@@ -72,10 +74,11 @@ class HostSim:
     self.l.hostsim_get_bodies(self.h, _p(out))
     return out
 
-  def step(self, actions=None):
+  def step(self, actions=None, pipeline=False):
+    """pipeline=True: the phase pipeline (csrc/blcd_pipeline.cuh), every phase in a fresh poisoned Sim, records through scratch"""
     a = None if actions is None else np.ascontiguousarray(actions, np.float32)
     out = np.zeros((self.n, self.A), np.float32)
-    self.l.hostsim_step(self.h, _p(a), _p(out))
+    (self.l.hostsim_step_pipeline if pipeline else self.l.hostsim_step)(self.h, _p(a), _p(out))
     return out
 
   def observe(self):
@@ -84,11 +87,11 @@ class HostSim:
     self.l.hostsim_observe(self.h, _p(fs), _p(bits))
     return {'full_state': fs, 'lcd_bits': bits}
 
-  def rollout(self, T):
+  def rollout(self, T, pipeline=False):
     fs = np.zeros((self.n, T, self.S), np.float32)
     bits = np.zeros((self.n, T) + self._rows(), np.uint32)
     act = np.zeros((self.n, T, self.A), np.float32)
-    self.l.hostsim_rollout(self.h, T, _p(fs), _p(bits), _p(act))
+    (self.l.hostsim_rollout_pipeline if pipeline else self.l.hostsim_rollout)(self.h, T, _p(fs), _p(bits), _p(act))
     return {'full_state': fs, 'lcd_bits': bits, 'action': act}
 
   def counters(self):

@@ -110,3 +110,35 @@ def test_open_world_floor_only_bit_exact(name):
   b = ow.get_bodies()
   assert np.isfinite(b).all() and b[..., 1].min() > 0.0          # nothing falls through the floor
   assert (b[..., 0] < 0).any() or (b[..., 0] > env.WIDTH).any()    # and nothing keeps the robots inside [0, WIDTH]
+
+
+@pytest.mark.parametrize('name', ALL)
+def test_phase_pipeline_rollouts_bit_exact(name):
+  """csrc/blcd_pipeline.cuh: the sub-step as five phases (setup / velocity / position / finish / TOI) with the records passed
+  through a per-world scratch buffer and a fresh, poisoned simulator object per phase -- the data flow between the
+  pipeline's kernels -- must reproduce the oracle bit for bit, counters included"""
+  env = make_env(name)
+  n, T = 24, 40
+  ow = oracle.OracleWorlds(env.layout.spec, n, seed=13, threads=4)
+  hs = HostSim(env.layout.spec, n, seed=13)
+  ow.reset(); hs.reset()
+  ro, rh = ow.rollout(T), hs.rollout(T, pipeline=True)
+  for k in ro:
+    assert (ro[k] == rh[k]).all(), k
+  assert (ow.get_bodies() == hs.get_bodies()).all()
+  assert (ow.counters() == hs.counters()).all()
+
+
+@pytest.mark.parametrize('name', ['Urchin', 'LuxoCube', 'Object2', 'CrabCube'])
+def test_phase_pipeline_single_steps_and_mixing_with_the_fused_path(name):
+  env = make_env(name)
+  rng = np.random.RandomState(6)
+  n = 64
+  bodies, variants = random_bodies(env, n, rng)
+  act = rng.uniform(-1.5, 1.5, (n, env.act_size)).astype(np.float32)
+  ow, hs = oracle.OracleWorlds(env.layout.spec, n), HostSim(env.layout.spec, n)
+  ow.set_bodies(bodies, variants); hs.set_bodies(bodies, variants)
+  for t in range(4):     # alternate the two paths on the same worlds: the persistent state is all that carries over
+    ow.step(act); hs.step(act, pipeline=(t % 2 == 0))
+    assert (ow.get_bodies() == hs.get_bodies()).all(), t
+  assert (ow.counters() == hs.counters()).all()
