@@ -32,7 +32,7 @@ BLCD_HD void pipe_pre(Sim<S>& sim, bool first, const float* action) {
   sim.x_jr_out(0, kHotJoint);
   sim.x_cr_out();
   sim.x_misc_out();
-  sim.store();
+  sim.store_after_setup();
 }
 
 // phase 2.  No load(): everything comes from the scratch area; impulses go to the manifold slots / scratch.
@@ -50,18 +50,33 @@ BLCD_HD void pipe_vel(Sim<S>& sim) {
 
 // phase 3.  Needs the shape variants (local centres, radii) besides the scratch records.
 template <int S>
-BLCD_HD void pipe_pos(Sim<S>& sim) {
+BLCD_HD void pipe_pos_begin(Sim<S>& sim) {
   sim.load_variant();
   sim.x_misc_in();
   sim.x_rows_in(3, 5);
   sim.x_cr_pk_in();
+  for (int k = 0; k < sim.nc; ++k) sim.pos_cache_manifold(k);   // manifold data is read once per world, not once per sweep
   sim.x_jr_in(J_MM, 1);
   sim.x_jr_in(J_PK, 2);       // packed limit state + J_REF
   sim.cnt[BLCD_CNT_POS_ITERS] = 0u;
-  sim.solve_position();
+  sim.islDone = 0u;
+}
+// word of the scratch area holding how many position sweeps the world needed last time (scheduling hint, see k_pipe_pos)
+BLCD_HD int pipe_prev_sweeps_word(const DScene& sc) { return sc.x_c0 - 1; }
+
+template <int S>
+BLCD_HD void pipe_pos_end(Sim<S>& sim, int sweeps = 0) {
+  sim.x.u(pipe_prev_sweeps_word(sim.scene())) = (uint32_t)sweeps;
   sim.x_rows_out(3, 3);
   sim.x.u(sim.scene().x_misc + 1) = sim.islDone;
   sim.g.u(sim.scene().off_cnt + BLCD_CNT_POS_ITERS) += sim.cnt[BLCD_CNT_POS_ITERS];
+}
+template <int S>
+BLCD_HD void pipe_pos(Sim<S>& sim) {
+  pipe_pos_begin(sim);
+  for (int it = 0; it < sim.scene().pos_iters; ++it)
+    if (sim.template solve_position_sweep<true>()) break;
+  pipe_pos_end(sim);
 }
 
 // phase 4.  Caller: sim.load() (poses / transforms before the solve = c0, a0, xf1).  Returns true if the world goes on to

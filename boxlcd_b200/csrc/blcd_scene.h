@@ -331,7 +331,7 @@ inline const char* build_scene(DScene& sc, const blcd_spec& sp, int maxm) {
   sc.x_rows = 0;
   sc.x_jr = sc.x_rows + 8 * sc.nb;
   sc.x_misc = sc.x_jr + kHotJoint * sc.nj;
-  sc.x_c0 = sc.x_misc + 2 + 2 * ((sc.nj + 3) / 4) + (sc.nb + 3) / 4;
+  sc.x_c0 = sc.x_misc + 3 + 2 * ((sc.nj + 3) / 4) + (sc.nb + 3) / 4;   // misc ends with one word that survives from sub-step to sub-step: the number of position sweeps the world last needed
   sc.x_cr = sc.x_c0 + 3 * sc.nb;
   sc.scratch_words = sc.x_cr + kHotCon * sc.maxm;
   return nullptr;

@@ -376,6 +376,34 @@ struct Sim {
     variant = kVariantInFlags ? ((g.u(sc.off_misc + 0) >> kVariantShift) & kBodyMask) : g.u(sc.off_misc + 4);
   }
 
+  // what the setup phase of the pipeline can have changed: flags (awake, new-fixture), sleep timers, the contact list, the
+  // motor speeds, counters, episode step and the draw counter -- not the body poses / velocities / AABBs, not the joint
+  // impulses (manifold slots are always written in place)
+  BLCD_HD void store_after_setup() {
+    const int nb = sc.nb;
+    if (kVariantInFlags) g.u(sc.off_misc + 0) = (awake & kAwakeMask) | (variant << kVariantShift) | (newFixture ? kNewFixtureBit : 0u);
+    else g.u(sc.off_misc + 0) = (awake & kAwakeMask) | (newFixture ? kNewFixtureBit : 0u);
+    g.u(sc.off_misc + 2) = (uint32_t)ep_t;
+    g.u(sc.off_misc + 3) = rng.draws;
+    for (int b = 0; b < kMaxBodies; ++b)
+      if (b < nb) g.f(kBodyWords * b + 6) = sleepT[b];
+    for (int j = 0; j < sc.nj; ++j) g.f(sc.off_joint + kJointWords * j + 4) = jr[kHotJoint * j + J_MS];
+    store_clist();
+    for (int k = 0; k < BLCD_N_COUNTERS; ++k) g.u(sc.off_cnt + k) = cnt[k];
+  }
+
+  BLCD_HD void store_clist() {
+    g.u(sc.off_clist) = (uint32_t)ncl;
+    for (int k4 = 0; k4 < sc.clist_words - 1; ++k4) {
+      uint32_t wd = 0u;
+      for (int k = 0; k < 4; ++k) {
+        int i = 4 * k4 + k;
+        if (i < ncl) wd |= (uint32_t)clist[i] << (8 * k);
+      }
+      g.u(sc.off_clist + 1 + k4) = wd;
+    }
+  }
+
   BLCD_HD void store() {
     const int nb = sc.nb;
     if (kVariantInFlags) {
@@ -873,12 +901,26 @@ struct Sim {
 
   // one pass of b2ContactSolver::SolvePositionConstraints / SolveTOIPositionConstraints over contact record k;
   // returns the smallest separation seen
-  BLCD_HD float contact_solve_position(int k, float baumgarte) {
+  // position-solve copy of a manifold inside the contact record (the words the velocity solve uses for its point records):
+  // the pipeline's position kernel reads the slot once per world instead of once per sweep (pos_cache_manifold)
+  enum { M_HDR = C_PT, M_LNX, M_LNY, M_LPX, M_LPY, M_P0X, M_P0Y, M_P1X, M_P1Y };
+  BLCD_HD void pos_cache_manifold(int k) {
+    const int h = kHotCon * k;
+    const int o = slot_base((int)((cru(h + C_PK) >> 12) & 255u));
+    cru(h + M_HDR) = g.u(o + S_HDR);
+    cr[h + M_LNX] = g.f(o + S_LNX); cr[h + M_LNY] = g.f(o + S_LNY); cr[h + M_LPX] = g.f(o + S_LPX); cr[h + M_LPY] = g.f(o + S_LPY);
+    cr[h + M_P0X] = g.f(o + S_PT); cr[h + M_P0Y] = g.f(o + S_PT + 1); cr[h + M_P1X] = g.f(o + S_PT + 5); cr[h + M_P1Y] = g.f(o + S_PT + 6);
+  }
+
+  BLCD_HD float contact_solve_position(int k, float baumgarte) { return contact_solve_position_t<false>(k, baumgarte); }
+
+  template <bool CACHED>
+  BLCD_HD float contact_solve_position_t(int k, float baumgarte) {
     const int h = kHotCon * k;
     uint32_t pk = cru(h + C_PK);
     int rA_ = pk & 31u, rB_ = (pk >> 5) & 31u, s = (pk >> 12) & 255u;
     const int o = slot_base(s);
-    uint32_t hdr = g.u(o + S_HDR);
+    uint32_t hdr = CACHED ? cru(h + M_HDR) : g.u(o + S_HDR);
     int p = (int)(hdr & 0xFFu), type = (int)((hdr >> 8) & 0xFFu), count = (int)((hdr >> 16) & 0xFFu);
     int fA, fB;
     pair_ab(p, &fA, &fB);
@@ -887,7 +929,9 @@ struct Sim {
     float mA = hm(rA_), iA = hi(rA_), mB = hm(rB_), iB = hi(rB_);
     V2 cA = hc(rA_), cB = hc(rB_);
     float aA = ha(rA_), aB = ha(rB_);
-    V2 ln = mk(g.f(o + S_LNX), g.f(o + S_LNY)), lp = mk(g.f(o + S_LPX), g.f(o + S_LPY));
+    V2 ln = CACHED ? mk(cr[h + M_LNX], cr[h + M_LNY]) : mk(g.f(o + S_LNX), g.f(o + S_LNY));
+    V2 lp = CACHED ? mk(cr[h + M_LPX], cr[h + M_LPY]) : mk(g.f(o + S_LPX), g.f(o + S_LPY));
+    V2 pt0 = CACHED ? mk(cr[h + M_P0X], cr[h + M_P0Y]) : mk(g.f(o + S_PT), g.f(o + S_PT + 1));
     float minSeparation = 0.0f;
     for (int j = 0; j < 2; ++j) {
       if (j < count) {
@@ -896,12 +940,12 @@ struct Sim {
         xfB.q = rB_ < nbS ? rot_of(aB) : rot_identity();
         xfA.p = cA - rmul(xfA.q, lcA);
         xfB.p = cB - rmul(xfB.q, lcB);
-        V2 lpt = mk(g.f(o + S_PT + 5 * j), g.f(o + S_PT + 5 * j + 1));
+        V2 lpt = j == 0 ? pt0 : (CACHED ? mk(cr[h + M_P1X], cr[h + M_P1Y]) : mk(g.f(o + S_PT + 5), g.f(o + S_PT + 6)));
         V2 normal, point;
         float separation;
         if (type == MF_CIRCLES) {
           V2 pointA = xmul(xfA, lp);
-          V2 pointB = xmul(xfB, mk(g.f(o + S_PT), g.f(o + S_PT + 1)));
+          V2 pointB = xmul(xfB, pt0);
           normal = pointB - pointA;
           normalize(normal);
           point = 0.5f * (pointA + pointB);
@@ -1343,23 +1387,34 @@ struct Sim {
   // position iterations; every island stops on its own convergence
   BLCD_HD void solve_position() {
     islDone = 0u;
+    // the manifolds are copied out of their HBM slots once (into the point-record words of the contact records, which
+    // the velocity phase no longer needs: its impulses are already stored) instead of being re-read every sweep
+    for (int k = 0; k < nc; ++k) pos_cache_manifold(k);
+    for (int it = 0; it < sc.pos_iters; ++it)
+      if (solve_position_sweep<true>()) break;
+  }
+
+  // one position iteration over the islands that have not converged yet; true when none is left.  (The pipeline's position
+  // kernel calls this once per loop trip for whatever world a lane currently holds, blcd_pipeline.cuh.)
+  template <bool CACHED = false>
+  BLCD_HD bool solve_position_sweep() {
     const uint32_t islAll = (1u << nIslands) - 1u;
-    for (int it = 0; it < sc.pos_iters && islDone != islAll; ++it) {
-      uint32_t bad = 0u;
-      cnt[BLCD_CNT_POS_ITERS] += (uint32_t)(nIslands - popc(islDone));
-      for (int k = 0; k < nc; ++k) {
-        int isl = (int)(cru(kHotCon * k + C_PK) >> 20);
-        if ((islDone >> isl) & 1u) continue;
-        float ms = contact_solve_position(k, kBaumgarte);
-        if (!(ms >= -3.0f * kLinearSlop)) bad |= 1u << isl;
-      }
-      for (int k = 0; k < njo; ++k) {
-        int isl = jisl[k];
-        if ((islDone >> isl) & 1u) continue;
-        if (!joint_solve_position(jorder[k])) bad |= 1u << isl;
-      }
-      islDone |= ~bad & islAll;
+    if (islDone == islAll) return true;
+    uint32_t bad = 0u;
+    cnt[BLCD_CNT_POS_ITERS] += (uint32_t)(nIslands - popc(islDone));
+    for (int k = 0; k < nc; ++k) {
+      int isl = (int)(cru(kHotCon * k + C_PK) >> 20);
+      if ((islDone >> isl) & 1u) continue;
+      float ms = contact_solve_position_t<CACHED>(k, kBaumgarte);
+      if (!(ms >= -3.0f * kLinearSlop)) bad |= 1u << isl;
     }
+    for (int k = 0; k < njo; ++k) {
+      int isl = jisl[k];
+      if ((islDone >> isl) & 1u) continue;
+      if (!joint_solve_position(jorder[k])) bad |= 1u << isl;
+    }
+    islDone |= ~bad & islAll;
+    return islDone == islAll;
   }
 
   // write back + SynchronizeTransform, sleeping, broad phase

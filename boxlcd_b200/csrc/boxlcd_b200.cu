@@ -260,15 +260,30 @@ __global__ void __launch_bounds__(BLOCK) k_observe(const DScene* scene_g, uint32
 // block-level synchronisation after the scene table is staged, so blocks and warps drift freely.
 constexpr int kPipeBlock = 128;
 // resident blocks per SM each phase kernel is compiled for (register cap = 65536 / (128 x blocks)) and given shared memory for
-constexpr int kPreBlocks = 4, kVelBlocks = 4, kPosBlocks = 6, kPostBlocks = 5, kToiBlocks = 3;
+constexpr int kPreBlocks = 4, kVelBlocks = 4, kPosBlocks = 4, kPostBlocks = 4, kToiBlocks = 4;
+constexpr int kPipeCarveBlocks = 4;   // every phase kernel asks for the same shared-memory carve-out, so kernels of different world ranges can share an SM
+// The velocity kernel takes its worlds in SORTED order: k_pipe_pre files every world under the key (touching contacts, how
+// many of them have two points), k_pipe_vel walks the bins from the busiest key down.  A warp then holds 32 worlds with the
+// same contact count, so the contact part of a velocity sweep runs with full warps instead of the warp's busiest lane
+// setting the trip count for everyone (7 of 32 lanes active before).  Any lane can take any world because everything the
+// velocity loop touches comes from the scratch area.
+constexpr int kVelBinsC = 8, kVelBinsP = 4, kVelBins = kVelBinsC * kVelBinsP;
+// The position kernel hands out worlds longest-first: sweep counts are heavy-tailed (mean ~8, up to 60) and a world tends to
+// need about as many sweeps as in its previous sub-step, so worlds are also filed by that count (kPosBins bins of 4 sweeps) and
+// fetched from the top bin down -- the stragglers start early and the cheap worlds fill the tail of the launch.
+constexpr int kPosBins = 16, kAllBins = kVelBins + kPosBins;
+__device__ __forceinline__ int vel_bin_key(int nc, int n2) {
+  return (nc < kVelBinsC ? nc : kVelBinsC - 1) * kVelBinsP + (n2 < kVelBinsP ? n2 : kVelBinsP - 1);
+}
 
 // mode 0: blcd_step (actions given or drawn; out.actions [N, A]); mode 1: blcd_rollout (obs_t and a_t recorded at row w T + t)
 __global__ void __launch_bounds__(kPipeBlock, kPreBlocks) k_pipe_pre(const DScene* scene_g, uint32_t* state, uint32_t* scratch, int64_t n, uint64_t seed, int64_t world_offset,
                                                             const float* actions, int mode, int T, int t, int first, OutPtrs out,
-                                                            int64_t w_begin, int64_t w_end, uint32_t* toi_count) {
+                                                            int64_t w_begin, int64_t w_end, uint32_t* toi_count, unsigned long long* pos_next,
+                                                            uint32_t* bin_count, uint32_t* bin_list) {
   unsigned char* smem_raw = blcd_smem;
   const DScene& sc = stage_scene<kPipeBlock>(scene_g, smem_raw);
-  if (blockIdx.x == 0 && threadIdx.x == 0) *toi_count = 0u;   // the list of this sub-step's TOI worlds starts empty
+  if (blockIdx.x == 0 && threadIdx.x == 0) { *toi_count = 0u; *pos_next = 0ull; }   // this sub-step's TOI list and position work counter start empty
   int64_t w = w_begin + (int64_t)blockIdx.x * kPipeBlock + threadIdx.x;
   if (w >= w_end) return;
   Sim<kPipeBlock> sim(sc, hot_base<kPipeBlock>(smem_raw), state, n, w, w_end);
@@ -290,32 +305,94 @@ __global__ void __launch_bounds__(kPipeBlock, kPreBlocks) k_pipe_pre(const DScen
     }
   }
   pipe_pre(sim, first != 0, act);
+  int n2 = 0;
+  for (int k = 0; k < sim.nc; ++k) n2 += ((sim.cru(kHotCon * k + C_PK) >> 10) & 3u) == 2u;
+  const int key = vel_bin_key(sim.nc, n2);
+  bin_list[(int64_t)key * n + w_begin + atomicAdd(bin_count + key, 1u)] = (uint32_t)(w - w_begin);
+  const uint32_t prev = sim.x.u(pipe_prev_sweeps_word(sc));
+  const int pkey = kVelBins + (int)(prev / 4u < (uint32_t)kPosBins ? prev / 4u : (uint32_t)kPosBins - 1u);
+  bin_list[(int64_t)pkey * n + w_begin + atomicAdd(bin_count + pkey, 1u)] = (uint32_t)(w - w_begin);
 }
 
-__global__ void __launch_bounds__(kPipeBlock, kVelBlocks) k_pipe_vel(const DScene* scene_g, uint32_t* state, uint32_t* scratch, int64_t n, int64_t w_begin, int64_t w_end) {
+__global__ void __launch_bounds__(kPipeBlock, kVelBlocks) k_pipe_vel(const DScene* scene_g, uint32_t* state, uint32_t* scratch, int64_t n, int64_t w_begin, int64_t w_end,
+                                                                     const uint32_t* bin_count, const uint32_t* bin_list) {
   unsigned char* smem_raw = blcd_smem;
   const DScene& sc = stage_scene<kPipeBlock>(scene_g, smem_raw);
-  int64_t w = w_begin + (int64_t)blockIdx.x * kPipeBlock + threadIdx.x;
-  if (w >= w_end) return;
+  int64_t i = (int64_t)blockIdx.x * kPipeBlock + threadIdx.x;
+  if (i >= w_end - w_begin) return;
+  // position i of the sorted order: bins from the busiest key down (the longest-running warps start first)
+  int64_t w = w_begin + i;
+  if (bin_list) {
+    int key = kVelBins - 1;
+    for (; key > 0; --key) {
+      const int64_t c = (int64_t)bin_count[key];
+      if (i < c) break;
+      i -= c;
+    }
+    w = w_begin + (int64_t)bin_list[(int64_t)key * n + w_begin + i];
+  }
   Sim<kPipeBlock> sim(sc, hot_base<kPipeBlock>(smem_raw), state, n, w, w_end);
   sim.attach_scratch(scratch, w);
   pipe_vel(sim);
 }
 
-__global__ void __launch_bounds__(kPipeBlock, kPosBlocks) k_pipe_pos(const DScene* scene_g, uint32_t* state, uint32_t* scratch, int64_t n, int64_t w_begin, int64_t w_end) {
+// Position iterations with LANES DECOUPLED FROM WORLDS.  A world needs anything from 0 to 60 sweeps (mean ~8-14): with one
+// world per lane a warp runs until its slowest world is done (4 of 32 lanes active on average).  Here the kernel is
+// persistent and every loop trip runs ONE sweep for whatever world each lane currently holds; a lane whose world has
+// converged writes it back and fetches the next unprocessed world from a global counter.  Everything a sweep needs is in
+// the lane's own shared-memory column / local records, filled from the scratch area, so any lane can take any world.
+__global__ void __launch_bounds__(kPipeBlock, kPosBlocks) k_pipe_pos(const DScene* scene_g, uint32_t* state, uint32_t* scratch, int64_t n, int64_t w_begin, int64_t w_end,
+                                                                     unsigned long long* next, int refill, const uint32_t* bin_count, const uint32_t* bin_list) {
   unsigned char* smem_raw = blcd_smem;
   const DScene& sc = stage_scene<kPipeBlock>(scene_g, smem_raw);
-  int64_t w = w_begin + (int64_t)blockIdx.x * kPipeBlock + threadIdx.x;
-  if (w >= w_end) return;
-  Sim<kPipeBlock> sim(sc, hot_base<kPipeBlock>(smem_raw), state, n, w, w_end);
-  sim.attach_scratch(scratch, w);
-  pipe_pos(sim);
+  Sim<kPipeBlock> sim(sc, hot_base<kPipeBlock>(smem_raw), state, n, w_begin);
+  const long long count = (long long)(w_end - w_begin);
+  bool have = false, exhausted = false;
+  int it = 0;
+  for (;;) {
+    // Refill in batches: fetching a world (filling its rows and records from the scratch area) is a few hundred instructions
+    // that only the fetching lanes execute, so lanes that ran out wait until `refill` of them are idle (or nobody has work)
+    // and then fetch together.
+    const unsigned idle = __ballot_sync(0xFFFFFFFFu, !have && !exhausted);
+    if (idle && (__popc(idle) >= refill || !__any_sync(0xFFFFFFFFu, have))) {
+      while (!have && !exhausted) {
+        long long idx = (long long)atomicAdd(next, 1ull);
+        if (idx >= count) { exhausted = true; break; }
+        int64_t w = w_begin + idx;
+        if (bin_list) {   // position idx of the longest-first order
+          int key = kPosBins - 1;
+          for (; key > 0; --key) {
+            const long long c = (long long)bin_count[kVelBins + key];
+            if (idx < c) break;
+            idx -= c;
+          }
+          w = w_begin + (int64_t)bin_list[(int64_t)(kVelBins + key) * n + w_begin + idx];
+        }
+        sim.g.p = state + w;
+        sim.attach_scratch(scratch, w);
+        pipe_pos_begin(sim);
+        it = 0;
+        have = sim.nIslands > 0 && sc.pos_iters > 0;
+        if (!have) pipe_pos_end(sim);
+      }
+    }
+    if (!__any_sync(0xFFFFFFFFu, have)) {
+      if (__all_sync(0xFFFFFFFFu, exhausted)) break;   // the whole warp is out of work and the queue is empty
+      continue;
+    }
+    if (have) {
+      bool done = sim.solve_position_sweep<true>();
+      ++it;
+      if (done || it >= sc.pos_iters) { pipe_pos_end(sim, it); have = false; }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kPipeBlock, kPostBlocks) k_pipe_post(const DScene* scene_g, uint32_t* state, uint32_t* scratch, int64_t n, uint64_t seed, int64_t world_offset,
-                                                             int64_t w_begin, int64_t w_end, uint32_t* toi_count, uint32_t* toi_list) {
+                                                             int64_t w_begin, int64_t w_end, uint32_t* toi_count, uint32_t* toi_list, uint32_t* bin_count) {
   unsigned char* smem_raw = blcd_smem;
   const DScene& sc = stage_scene<kPipeBlock>(scene_g, smem_raw);
+  if (blockIdx.x == 0 && threadIdx.x < kAllBins) bin_count[threadIdx.x] = 0u;   // consumed by k_pipe_vel; refilled by the next k_pipe_pre
   int64_t w = w_begin + (int64_t)blockIdx.x * kPipeBlock + threadIdx.x;
   if (w >= w_end) return;
   Sim<kPipeBlock> sim(sc, hot_base<kPipeBlock>(smem_raw), state, n, w, w_end);
@@ -459,6 +536,12 @@ struct BLCD_PENV {
   uint32_t* scratch = nullptr;      // [scratch_words][n]
   uint32_t* toi_count = nullptr;    // [kHostStreams] one counter per concurrently processed world range
   uint32_t* toi_list = nullptr;     // [n] range-relative world indices that need SolveTOI in the current sub-step
+  unsigned long long* pos_next = nullptr;   // [kHostStreams] work counters of the persistent position kernel
+  uint32_t* bin_count = nullptr;    // [kHostStreams][kVelBins] worlds per velocity-sort key in the current sub-step
+  uint32_t* bin_list = nullptr;     // [kVelBins][n] range-relative world indices filed under each key
+  int sm_count = 148;
+  cudaStream_t pstream[kHostStreams] = {};   // world ranges of one pipeline call run on streams of their own
+  cudaEvent_t pev[kHostStreams] = {}, pev_begin = nullptr;
 };
 
 namespace {
@@ -532,6 +615,7 @@ int BLCD_P(create)(const blcd_spec* spec_host, int64_t n_worlds, int device, uin
   //    448-thread blocks instead of two of 256 (+33 %), 262 144 take 4 waves instead of 7 (+17 %).
   int sm_count = 148;
   CK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+  h->sm_count = sm_count;
   //  * few worlds (less than one 256-thread block per SM): smaller blocks, so that more SMs have one -- a block's time
   //    shrinks only a little with its size (128 threads: 0.83 of 256), but 4 096 worlds then use 64 SMs instead of 16.
   h->block = 256;
@@ -553,6 +637,13 @@ int BLCD_P(create)(const blcd_spec* spec_host, int64_t n_worlds, int device, uin
     }
   }
   if (const char* e = getenv("BLCD_BLOCK")) h->block = atoi(e);
+  // Which device path steps this handle's worlds (both give the same results up to FMA-contraction-level round-off; each is
+  // deterministic and independent of how the worlds are sharded):
+  //  * the phase pipeline (blcd_pipeline.cuh) once there are enough worlds to fill the GPU in every phase -- measured on a
+  //    B200 (Urchin): 19.2 M env-steps/s against 14.9 M at 131 072 worlds, 26.2 M against 16.4 M at 262 144, but 12.8 M against
+  //    14.7 M at 65 536 (its five kernels per sub-step each need their own wave of worlds);
+  //  * the fused one-thread-per-world kernel below that, and for single environments.
+  h->pipeline = n_worlds >= 98304;
   if (const char* e = getenv("BLCD_PIPELINE")) h->pipeline = atoi(e) != 0;
   {
 #if BLCD_PROFILE_ID == 0
@@ -629,7 +720,10 @@ int BLCD_P(destroy)(BLCD_PENV* h) {
   if (h->h_bits) cudaFreeHost(h->h_bits);
   if (h->h_done) cudaFreeHost(h->h_done);
   cudaFree(h->d_act); cudaFree(h->d_fs); cudaFree(h->d_bits); cudaFree(h->d_done);
-  cudaFree(h->scratch); cudaFree(h->toi_count); cudaFree(h->toi_list);
+  for (auto& s : h->pstream) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+  for (auto& e : h->pev) if (e) cudaEventDestroy(e);
+  if (h->pev_begin) cudaEventDestroy(h->pev_begin);
+  cudaFree(h->scratch); cudaFree(h->toi_count); cudaFree(h->toi_list); cudaFree(h->pos_next); cudaFree(h->bin_count); cudaFree(h->bin_list);
   for (auto& r : h->pinned_user) cudaHostUnregister(const_cast<void*>(r.first));
   for (auto& ring : h->hev) for (auto& e : ring) if (e) cudaEventDestroy(e);
   delete h;
@@ -709,38 +803,87 @@ int BLCD_P(get_poses)(BLCD_PENV* h, float* poses_dev, uint32_t* variant_dev, uin
 static int pipeline_prepare(BLCD_PENV* h) {
   if (h->scratch) return 0;
   CK(cudaMalloc(&h->scratch, (size_t)h->scene.scratch_words * (size_t)h->n * 4));
+  CK(cudaMemset(h->scratch, 0, (size_t)h->scene.scratch_words * (size_t)h->n * 4));   // the sweep-count hints start at zero
   CK(cudaMalloc(&h->toi_count, kHostStreams * sizeof(uint32_t)));
   CK(cudaMemset(h->toi_count, 0, kHostStreams * sizeof(uint32_t)));
   CK(cudaMalloc(&h->toi_list, (size_t)h->n * sizeof(uint32_t)));
+  CK(cudaMalloc(&h->bin_count, kHostStreams * kAllBins * sizeof(uint32_t)));
+  CK(cudaMemset(h->bin_count, 0, kHostStreams * kAllBins * sizeof(uint32_t)));
+  CK(cudaMalloc(&h->bin_list, (size_t)kAllBins * (size_t)h->n * sizeof(uint32_t)));
+  CK(cudaMalloc(&h->pos_next, kHostStreams * sizeof(unsigned long long)));
+  CK(cudaMemset(h->pos_next, 0, kHostStreams * sizeof(unsigned long long)));
   const size_t sb = smem_bytes(h, kPipeBlock);
-  if (set_smem_attr(k_pipe_pre, sb, kPreBlocks) || set_smem_attr(k_pipe_vel, sb, kVelBlocks) || set_smem_attr(k_pipe_pos, sb, kPosBlocks) ||
-      set_smem_attr(k_pipe_post, sb, kPostBlocks) || set_smem_attr(k_pipe_toi, sb, kToiBlocks))
+  if (set_smem_attr(k_pipe_pre, sb, kPipeCarveBlocks) || set_smem_attr(k_pipe_vel, sb, kPipeCarveBlocks) || set_smem_attr(k_pipe_pos, sb, kPipeCarveBlocks) ||
+      set_smem_attr(k_pipe_post, sb, kPipeCarveBlocks) || set_smem_attr(k_pipe_toi, sb, kPipeCarveBlocks))
     return -1;
+  for (int r = 0; r < kHostStreams; ++r) {
+    if (!h->pstream[r]) CK(cudaStreamCreateWithFlags(&h->pstream[r], cudaStreamNonBlocking));
+    if (!h->pev[r]) CK(cudaEventCreateWithFlags(&h->pev[r], cudaEventDisableTiming));
+  }
+  if (!h->pev_begin) CK(cudaEventCreateWithFlags(&h->pev_begin, cudaEventDisableTiming));
   return 0;
 }
 
 // T env steps of worlds [w0, w1) on stream st: per sub-step five launches.  mode 0: blcd_step semantics (actions_dev or the
 // device RNG, T == 1); mode 1: blcd_rollout semantics (obs_t / a_t recorded before step t).  `slot`: which TOI counter to
 // use (ranges running concurrently on different streams need their own).
-static int pipeline_run(BLCD_PENV* h, const float* actions_dev, int mode, int T, OutPtrs out, cudaStream_t st, int64_t w0, int64_t w1, int slot) {
-  if (pipeline_prepare(h)) return -1;
-  if (w1 <= w0) return 0;
+// one sub-step (five launches) of worlds [w0, w1) on stream st
+static void pipeline_substep(BLCD_PENV* h, const float* actions_dev, int mode, int T, int t, int s, OutPtrs out, cudaStream_t st, int64_t w0, int64_t w1, int slot) {
   const unsigned blocks = (unsigned)((w1 - w0 + kPipeBlock - 1) / kPipeBlock);
   const size_t sb = smem_bytes(h, kPipeBlock);
   uint32_t* cnt = h->toi_count + slot;
   uint32_t* list = h->toi_list + w0;
-  for (int t = 0; t < T; ++t) {
-    for (int s = 0; s < h->scene.nsub; ++s) {
+  uint32_t* bins = h->bin_count + slot * kAllBins;
+  // the position kernel is persistent: as many blocks as can be resident, never more than there are worlds for
+  static const int pos_resident = getenv("BLCD_POS_BLOCKS") ? atoi(getenv("BLCD_POS_BLOCKS")) : kPosBlocks;
+  unsigned pos_blocks = (unsigned)(h->sm_count * (pos_resident < 1 ? 1 : (pos_resident > kPosBlocks ? kPosBlocks : pos_resident)));
+  if (pos_blocks > blocks) pos_blocks = blocks;
+  static const bool pos_sort = !(getenv("BLCD_POS_SORT") && atoi(getenv("BLCD_POS_SORT")) == 0);
+  static const int pos_refill = getenv("BLCD_POS_REFILL") ? atoi(getenv("BLCD_POS_REFILL")) : 16;
+  {
+    {
       k_pipe_pre<<<blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, h->seed, h->world_offset, actions_dev, mode, T, t, s == 0 ? 1 : 0, out,
-                                                 w0, w1, cnt);
-      k_pipe_vel<<<blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, w0, w1);
-      k_pipe_pos<<<blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, w0, w1);
-      k_pipe_post<<<blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, h->seed, h->world_offset, w0, w1, cnt, list);
+                                                 w0, w1, cnt, h->pos_next + slot, bins, h->bin_list);
+      static const bool vel_sort = !(getenv("BLCD_VEL_SORT") && atoi(getenv("BLCD_VEL_SORT")) == 0);
+      k_pipe_vel<<<blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, w0, w1, bins, vel_sort ? h->bin_list : nullptr);
+      k_pipe_pos<<<pos_blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, w0, w1, h->pos_next + slot, pos_refill, bins, pos_sort ? h->bin_list : nullptr);
+      k_pipe_post<<<blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, h->seed, h->world_offset, w0, w1, cnt, list, bins);
       k_pipe_toi<<<blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, h->seed, h->world_offset, w0, cnt, list);
       h->launches += 5;
     }
   }
+}
+
+// T env steps of worlds [w0, w1), ordered after / before the work on stream st.  The worlds are split into up to kHostStreams
+// ranges, each on a stream of its own with its own TOI list / sort bins / work counter, and the launches of the ranges are
+// interleaved: while one range sits in a latency-bound phase (narrow phase, TOI, the tail of any kernel) another range's
+// velocity kernel fills the SMs.  `slot0`: first counter slot to use (blcd_step_host's concurrent sub-ranges pass theirs).
+static int pipeline_run(BLCD_PENV* h, const float* actions_dev, int mode, int T, OutPtrs out, cudaStream_t st, int64_t w0, int64_t w1, int slot0, int max_ranges = kHostStreams) {
+  if (pipeline_prepare(h)) return -1;
+  if (w1 <= w0) return 0;
+  static const int want = getenv("BLCD_PIPE_RANGES") ? atoi(getenv("BLCD_PIPE_RANGES")) : 2;
+  int R = want < 1 ? 1 : (want > max_ranges ? max_ranges : want);
+  const int64_t gran = 4 * kPipeBlock;
+  while (R > 1 && (w1 - w0) / R < 98304) --R;    // small ranges cannot fill the GPU: the interleaving only pays with enough worlds each
+  if (R == 1) {
+    for (int t = 0; t < T; ++t)
+      for (int s = 0; s < h->scene.nsub; ++s) pipeline_substep(h, actions_dev, mode, T, t, s, out, st, w0, w1, slot0);
+    CK(cudaGetLastError());
+    return 0;
+  }
+  CK(cudaEventRecord(h->pev_begin, st));
+  for (int r = 0; r < R; ++r) CK(cudaStreamWaitEvent(h->pstream[r], h->pev_begin, 0));
+  for (int t = 0; t < T; ++t)
+    for (int s = 0; s < h->scene.nsub; ++s)
+      for (int r = 0; r < R; ++r) {
+        const int64_t a = w0 + ((w1 - w0) * r / R) / gran * gran, b = r + 1 == R ? w1 : w0 + ((w1 - w0) * (r + 1) / R) / gran * gran;
+        if (b > a) pipeline_substep(h, actions_dev, mode, T, t, s, out, h->pstream[r], a, b, slot0 + r);
+      }
   CK(cudaGetLastError());
+  for (int r = 0; r < R; ++r) {
+    CK(cudaEventRecord(h->pev[r], h->pstream[r]));
+    CK(cudaStreamWaitEvent(st, h->pev[r], 0));
+  }
   return 0;
 }
 
@@ -749,7 +892,7 @@ static int step_range(BLCD_PENV* h, const float* actions_dev, int n_steps, OutPt
     OutPtrs o = out;
     OutPtrs act_only = {nullptr, nullptr, nullptr, nullptr, nullptr, out.actions};
     for (int i = 0; i < n_steps; ++i)
-      if (pipeline_run(h, actions_dev, 0, 1, act_only, st, w_begin, w_end, slot)) return -1;
+      if (pipeline_run(h, actions_dev, 0, 1, act_only, st, w_begin, w_end, slot, w_begin == 0 && w_end == h->n ? kHostStreams : 1)) return -1;
     o.actions = nullptr;
     if (o.full_state || o.proprio || o.lcd_bits || o.lcd_bool || o.done) {
       int rc = launch_sized(h, [&](auto B) {
@@ -926,7 +1069,9 @@ static int host_chunks_default(BLCD_PENV* h) {
     h->host_chunks_env = e ? atoi(e) : 0;
   }
   if (h->host_chunks_env > 0) return h->host_chunks_env;
-  return h->timing ? 1 : kHostStreams;
+  if (h->timing) return 1;
+  if (h->pipeline) return h->n >= 4 * 98304 ? 4 : (h->n >= 2 * 98304 ? 2 : 1);   // every range must still fill the GPU phase by phase
+  return kHostStreams;
 }
 
 int BLCD_P(step_host)(BLCD_PENV* h, const float* actions_host, float* full_state_host, uint32_t* lcd_bits_host, uint8_t* done_host) {

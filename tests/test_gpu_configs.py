@@ -373,3 +373,49 @@ def test_rgb_mode_and_human_frame_through_the_env_api():
   big = env.lcd_render(192, 128, lcd_mode='RGB')
   assert (img[:, :192] == big).all()
   env.close()
+
+
+@pytest.mark.parametrize('name', ['Urchin', 'LuxoCube', 'Bounce2', 'CrabCube'])
+def test_phase_pipeline_and_fused_kernel_agree(name, monkeypatch):
+  """The two device paths (csrc/blcd_pipeline.cuh: five kernels per sub-step through HBM scratch; the fused one-thread-per-world
+  kernel) run the same phase functions in the same order: identical action streams and counters' structure, states equal up to
+  FMA-contraction-level round-off -- each as close to the oracle as the other (tests/test_gpu_parity.py bars)."""
+  env = make_env(name)
+  n, T = 4096, 4
+  outs = {}
+  for pipeline in ('0', '1'):
+    monkeypatch.setenv('BLCD_PIPELINE', pipeline)
+    v = vec(env, n, seed=21)
+    v.reset_dev()
+    r = v.rollout_dev(T)
+    outs[pipeline] = {k: x.cpu().numpy() for k, x in r.items()}
+    outs[pipeline]['counters'] = v.counters()
+    assert v.counters()[:, 5].sum() == 0
+  a, b = outs['0'], outs['1']
+  assert (a['action'] == b['action']).all()
+  assert (a['full_state'][:, 0] == b['full_state'][:, 0]).all(), 'the reset state does not depend on the path'
+  big = env.layout.spec.n_bodies > 8
+  close = (np.abs(a['full_state'][:, 1] - b['full_state'][:, 1]).max(1) < (5e-5 if big else 1e-5)).mean()
+  assert close > (0.97 if big else 0.99), close
+  assert (a['counters'][:, 7] == b['counters'][:, 7]).all()     # sub-steps taken
+  ow = oracle.OracleWorlds(env.layout.spec, n, seed=21, threads=8)
+  ow.reset()
+  ref = ow.rollout(T)['full_state']
+  for k in ('0', '1'):
+    ok = (np.abs(outs[k]['full_state'][:, 1] - ref[:, 1]).max(1) < (5e-5 if big else 1e-5)).mean()
+    assert ok > (0.97 if big else 0.98), (k, ok)
+
+
+def test_phase_pipeline_is_sharding_invariant(monkeypatch):
+  """worlds keyed by global index: a pipeline shard reproduces its slice of the full batch bit for bit, whatever the world ranges /
+  streams the launches were split into"""
+  monkeypatch.setenv('BLCD_PIPELINE', '1')
+  env = make_env('UrchinBall')
+  full = vec(env, 3000, seed=9); full.reset_dev(); f = full.rollout_dev(6)
+  part = vec(env, 1000, seed=9, world_offset=1500); part.reset_dev(); p = part.rollout_dev(6)
+  for k in f:
+    assert torch.equal(f[k][1500:2500], p[k]), k
+  a = torch.rand((3000, 3), device='cuda') * 2 - 1
+  of, _ = full.step_dev(a, observe=True)
+  op, _ = part.step_dev(a[1500:2500].contiguous(), observe=True)
+  assert torch.equal(of['full_state'][1500:2500], op['full_state']) and torch.equal(of['lcd_bits'][1500:2500], op['lcd_bits'])

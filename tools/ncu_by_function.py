@@ -1,5 +1,7 @@
 """Aggregate an ncu report's SASS-level counters by CUDA source function (needs -lineinfo):
-   python tools/ncu_by_function.py <report.ncu-rep> <lib.so> <kernel-substring>"""
+   python tools/ncu_by_function.py <report.ncu-rep | prefix of pre-dumped pages> <lib.so> <kernel-substring>
+With a prefix P the pages are read from P.raw.csv / P.source.csv (`ncu -i rep --page raw|source --csv`, dumped on the GPU box:
+the reports themselves are too large to bring back)."""
 import collections, csv, os, re, subprocess, sys, tempfile
 rep, so, kname = sys.argv[1], sys.argv[2], sys.argv[3]
 tmp = tempfile.mkdtemp()
@@ -11,7 +13,11 @@ for cubin in sorted(f for f in os.listdir(tmp) if f.endswith('.cubin')):
   if any(l.startswith('.text.') and all(k in l for k in kname.split('+')) for l in d):
     dis = d
     break
-raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+def page(name):
+  if rep.endswith('.ncu-rep'):
+    return subprocess.run(['ncu', '-i', rep, '--page', name, '--csv'], capture_output=True, text=True).stdout
+  return open(f'{rep}.{name}.csv').read()
+raw = page('raw')
 rows = list(csv.reader(raw.split('\n')))
 hdr, vals = rows[0], rows[2]
 get = lambda k: vals[hdr.index(k)]
@@ -22,7 +28,7 @@ for k in ['gpu__time_duration.sum', 'smsp__inst_executed.sum', 'smsp__thread_ins
           'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio',
           'smsp__average_warp_latency_per_inst_issued.ratio', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'sass__inst_executed_local_loads', 'sass__inst_executed_shared_loads', 'sass__inst_executed_global_loads']:
   if k in hdr: print(f'{k:90s} {get(k)}')
-srcrows = list(csv.reader(subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout.split('\n')))
+srcrows = list(csv.reader(page('source').split('\n')))
 kfull = srcrows[0][1]
 start = [i for i, l in enumerate(dis) if l.startswith('.text.') and all(k in l for k in kname.split('+'))][0]
 off2loc, cur = {}, ('?', 0)
