@@ -194,7 +194,7 @@ def workload_name(env_name, sp, total, T):
   return f'envs.{env_name}() {sp.lcd_h}x{sp.lcd_w}, {total} worlds in total, random-action {T}-step rollouts (reset + step + obs + frame)'
 
 
-def ncu_instruction_count(env_name, n, T, timeout=240):
+def ncu_instruction_count(env_name, n, T, pipeline, timeout=300):
   """Count, IN THIS RUN, the instructions of one rollout: an `ncu --metrics` sub-process profiles every kernel this library
   launches for one T-step rollout of n worlds (tools/ncu_case.py brackets it with cudaProfilerStart/Stop) and the
   per-kernel counters are summed.  Returns None when ncu is unavailable (then nothing is reported -- no static copy)."""
@@ -202,7 +202,8 @@ def ncu_instruction_count(env_name, n, T, timeout=240):
   cmd = ['ncu', '--csv', '--profile-from-start', 'off', '--clock-control', 'none', '--metrics', metrics,
          sys.executable, os.path.join(ROOT, 'tools', 'ncu_case.py'), env_name, str(n), str(T), 'range']
   try:
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    # the sub-process must take the same device path as the timed handle (the library picks it from the world count)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=dict(os.environ, BLCD_PIPELINE=str(int(pipeline))))
   except Exception as e:
     return {'unavailable': f'{type(e).__name__}: {e}'[:200]}
   text = res.stdout
@@ -231,6 +232,7 @@ def ncu_instruction_count(env_name, n, T, timeout=240):
           'active_lanes_per_warp_inst': tot['smsp__thread_inst_executed.sum'] / max(tot['smsp__inst_executed.sum'], 1.0),
           'dram_bytes_per_env_step': (tot.get('dram__bytes_read.sum', 0.0) + tot.get('dram__bytes_write.sum', 0.0)) / steps,
           'kernel_seconds_under_ncu': {k: v for k, v in sorted(kernels.items(), key=lambda kv: -kv[1])[:8]},
+          'kernel_share_of_gpu_time_under_ncu': {k: v / max(sum(kernels.values()), 1e-12) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1])[:8]},
           'source': 'ncu sub-process of this bench run (cold caches, serialised kernels): counts, not times, are used'}
 
 
@@ -434,7 +436,7 @@ def main():
   counts = None
   if not a.no_ncu:
     torch.cuda.synchronize()
-    counts = ncu_instruction_count(a.env, min(n, 37888), 3)
+    counts = ncu_instruction_count(a.env, min(n, 131072), 2, info.get('pipeline', 0))
   per_gpu_rate = n * T / (k_ms / 1e3)      # env-steps/s of this GPU inside the rollout launch(es)
   solver = {'bound': 'issue', 'unit': 'lane-instructions/s', 'peak': lane_peak,
             'peak_source': 'blcd_measure_peaks in this run: fp32 FMA with every issue slot filled (x2 = %.1f TFLOP/s fp32)' % (2 * lane_peak / 1e12),

@@ -507,6 +507,69 @@ __global__ void __launch_bounds__(kRenderThreads) k_render_poses(const DScene* s
   for (int k = 0, lw = row_words(win_w); k < lw; ++k) bits[(w * lcd_h + R) * row_stride + word_off + k] = row_word(out, k);
 }
 
+// lcd_render, second formulation: ONE LANE PER (frame, body), lanes ordered body-major inside a block of kR2Frames frames.
+// Consecutive lanes then hold the SAME body of consecutive frames -- the same shape kind, vertex count and size, hence the
+// same code path and nearly the same number of rows -- so warps stay converged through the scanline rules, where the
+// (frame, row)-per-lane kernel above mixes circles, polygons and empty rows in every warp (7.9 of 32 lanes active).  A lane
+// sets its body up once (vertex transform, metre -> pixel scaling), walks the body's rows and ORs each row's ink into the
+// frame's row masks in shared memory; the block then writes the kR2Frames x H packed rows with coalesced stores.
+// Poses come either from a pose array [n, nb, 4] (blcd_render_poses) or straight from the simulation state (the rollout
+// pipeline renders obs_t this way: frame w goes to output frame w * frame_mul + frame_add).
+constexpr int kR2Frames = 64, kR2Threads = 256;
+__global__ void __launch_bounds__(kR2Threads) k_render_bodies(const DScene* scene_g, const float* poses, const uint32_t* variants, const uint32_t* state, int64_t n_state,
+                                                              int64_t w_begin, int64_t n, int lcd_w, int lcd_h, uint32_t* bits, int x_off, int win_w, int row_stride, int word_off,
+                                                              int64_t frame_mul, int64_t frame_add) {
+  extern __shared__ __align__(16) unsigned char rsm[];
+  DScene* scp = reinterpret_cast<DScene*>(rsm);
+  RowInk* rowink = reinterpret_cast<RowInk*>(rsm + kSceneBytes);
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(scene_g);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(scp);
+    for (int i = threadIdx.x; i < (int)(sizeof(DScene) / 4); i += kR2Threads) dst[i] = src[i];
+    for (int i = threadIdx.x; i < kR2Frames * lcd_h; i += kR2Threads) rowink[i] = 0u;
+    __syncthreads();
+  }
+  const DScene& sc = *scp;
+  const int64_t f0 = (int64_t)blockIdx.x * kR2Frames;
+  const float* sf = reinterpret_cast<const float*>(state);
+  for (int item = threadIdx.x; item < kR2Frames * sc.nb; item += kR2Threads) {
+    const int b = item / kR2Frames, f = item - b * kR2Frames;
+    const int64_t i = f0 + f;
+    if (i >= n) continue;
+    float px, py, sn, cs;
+    uint32_t variant;
+    if (state) {
+      const int64_t w = w_begin + i;
+      const int o = kBodyWords * b;
+      px = sf[(int64_t)(o + 11) * n_state + w]; py = sf[(int64_t)(o + 12) * n_state + w];
+      Rot q = rot_of(sf[(int64_t)(o + 2) * n_state + w]);
+      sn = q.s; cs = q.c;
+      variant = kVariantInFlags ? ((state[(int64_t)sc.off_misc * n_state + w] >> kVariantShift) & kBodyMask) : state[(int64_t)(sc.off_misc + 4) * n_state + w];
+    } else {
+      const float* p = poses + (i * sc.nb + b) * 4;
+      px = p[0]; py = p[1]; sn = p[2]; cs = p[3];
+      variant = variants ? variants[i] : 0u;
+    }
+    BodyPx bp;
+    body_px(bp, sc.body[b].shape[(variant >> b) & 1u], px, py, sn, cs, sc.world_w, lcd_w);
+    const int ylo = max(bp.y0, 0), yhi = min(bp.y1, lcd_h - 1);
+    for (int y = ylo; y <= yhi; ++y) {
+      RowMask m = body_px_row(bp, y, win_w, lcd_h, sc.rules, x_off);
+      if (m) atomicOr(&rowink[f * lcd_h + y], (RowInk)m);
+    }
+  }
+  __syncthreads();
+  const int lw = row_words(win_w);
+  for (int j = threadIdx.x; j < kR2Frames * lcd_h; j += kR2Threads) {
+    const int f = j / lcd_h, R = j - f * lcd_h;
+    const int64_t i = f0 + f;
+    if (i >= n) continue;
+    const RowMask out = row_bits_from_ink((RowMask)rowink[f * lcd_h + (lcd_h - 1 - R)], win_w);
+    const int64_t frame = i * frame_mul + frame_add;
+    for (int k = 0; k < lw; ++k) __stcs(bits + (frame * lcd_h + R) * row_stride + word_off + k, row_word(out, k));
+  }
+}
+
 }  // namespace
 
 constexpr int kHostStreams = 8;
@@ -555,6 +618,11 @@ int launch_sized(BLCD_PENV* h, F f) {
     case 64: return f(std::integral_constant<int, 64>());
 #endif
     case 128: return f(std::integral_constant<int, 128>());
+#if BLCD_PROFILE_ID == 0
+    case 160: return f(std::integral_constant<int, 160>());
+    case 192: return f(std::integral_constant<int, 192>());
+    case 224: return f(std::integral_constant<int, 224>());
+#endif
     case 256: return f(std::integral_constant<int, 256>());
 #if BLCD_PROFILE_ID == 0   // the large profile is only ever launched with 256 threads (or 128 as the shared-memory fallback)
     case 320: return f(std::integral_constant<int, 320>());
@@ -618,8 +686,14 @@ int BLCD_P(create)(const blcd_spec* spec_host, int64_t n_worlds, int device, uin
   h->sm_count = sm_count;
   //  * few worlds (less than one 256-thread block per SM): smaller blocks, so that more SMs have one -- a block's time
   //    shrinks only a little with its size (128 threads: 0.83 of 256), but 4 096 worlds then use 64 SMs instead of 16.
+  //  * between one half and one full wave of 256-thread blocks: the smallest block size that still gives every SM at most one
+  //    block, so that all SMs work -- 32 768 worlds (262 144 split over 8 GPUs) are 128 blocks of 256 threads, i.e. 20 idle
+  //    SMs, but 147 blocks of 224.
   h->block = 256;
-  if (n_worlds <= (int64_t)sm_count * 128) {
+  if (n_worlds > (int64_t)sm_count * 128 && n_worlds < (int64_t)sm_count * 256 && BLCD_PROFILE_ID == 0) {
+    for (int b : {160, 192, 224})
+      if ((n_worlds + b - 1) / b <= sm_count) { h->block = b; break; }
+  } else if (n_worlds <= (int64_t)sm_count * 128) {
 #if BLCD_PROFILE_ID == 0
     h->block = n_worlds <= (int64_t)sm_count * 64 ? 64 : 128;
 #else
@@ -647,7 +721,7 @@ int BLCD_P(create)(const blcd_spec* spec_host, int64_t n_worlds, int device, uin
   if (const char* e = getenv("BLCD_PIPELINE")) h->pipeline = atoi(e) != 0;
   {
 #if BLCD_PROFILE_ID == 0
-    const int sizes[] = {512, 448, 384, 320, 256, 128, 64};
+    const int sizes[] = {512, 448, 384, 320, 256, 224, 192, 160, 128, 64};
 #else
     const int sizes[] = {256, 128};
 #endif
@@ -842,6 +916,21 @@ static void pipeline_substep(BLCD_PENV* h, const float* actions_dev, int mode, i
   static const int pos_refill = getenv("BLCD_POS_REFILL") ? atoi(getenv("BLCD_POS_REFILL")) : 16;
   {
     {
+      if (mode == 1 && s == 0 && out.lcd_bits) {
+        // obs_t's frame: rendered from the state as it is before step t by the body-major render kernel (3x the lanes of the
+        // per-thread renderer inside k_pipe_pre); k_pipe_pre then records full_state and the action only
+        if (!h->render_attr_set) {
+          cudaFuncSetAttribute(k_render_poses, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kSceneBytes + sizeof(BodyPx) * kMaxBodies * kRenderMaxFrames + sizeof(RowInk) * kRenderThreads));
+          cudaFuncSetAttribute(k_render_bodies, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kSceneBytes + sizeof(RowInk) * kR2Frames * 256));
+          h->render_attr_set = true;
+        }
+        const int64_t cnt_w = w1 - w0;
+        k_render_bodies<<<(unsigned)((cnt_w + kR2Frames - 1) / kR2Frames), kR2Threads, (size_t)kSceneBytes + sizeof(RowInk) * kR2Frames * (size_t)h->scene.lcd_h, st>>>(
+            h->scene_dev, nullptr, nullptr, h->state, h->n, w0, cnt_w, h->scene.lcd_w, h->scene.lcd_h, out.lcd_bits + (size_t)w0 * T * h->scene.lcd_h * row_words(h->scene.lcd_w),
+            0, h->scene.lcd_w, row_words(h->scene.lcd_w), 0, T, t);
+        h->launches += 1;
+        out.lcd_bits = nullptr;
+      }
       k_pipe_pre<<<blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, h->seed, h->world_offset, actions_dev, mode, T, t, s == 0 ? 1 : 0, out,
                                                  w0, w1, cnt, h->pos_next + slot, bins, h->bin_list);
       static const bool vel_sort = !(getenv("BLCD_VEL_SORT") && atoi(getenv("BLCD_VEL_SORT")) == 0);
@@ -1152,18 +1241,24 @@ int BLCD_P(render_poses_sized)(BLCD_PENV* h, const float* poses_dev, const uint3
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (lcd_h > kRenderThreads) return fail("blcd_render_poses: frame height out of range");
+  static const bool old_kernel = getenv("BLCD_RENDER_ROWS") && atoi(getenv("BLCD_RENDER_ROWS")) != 0;   // (frame, row)-per-lane kernel, kept for comparison
   const int fpb = render_frames_per_block(lcd_h);
   const size_t rsm_bytes = (size_t)kSceneBytes + sizeof(BodyPx) * kMaxBodies * (size_t)fpb + sizeof(RowInk) * (size_t)kRenderThreads;
   if (!h->render_attr_set) {
     CK(cudaFuncSetAttribute(k_render_poses, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kSceneBytes + sizeof(BodyPx) * kMaxBodies * kRenderMaxFrames + sizeof(RowInk) * kRenderThreads)));
+    CK(cudaFuncSetAttribute(k_render_bodies, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kSceneBytes + sizeof(RowInk) * kR2Frames * 256)));
     h->render_attr_set = true;
   }
   if (begin_timing(h, st)) return -1;
   const int row_stride = row_words(lcd_w);
   for (int x_off = 0; x_off < lcd_w; x_off += kRowBits) {   // one launch per column window of kRowBits pixels
     const int win_w = lcd_w - x_off < kRowBits ? lcd_w - x_off : kRowBits;
-    k_render_poses<<<(unsigned)((n + fpb - 1) / fpb), kRenderThreads, rsm_bytes, st>>>(h->scene_dev, poses_dev, variant_dev, n, lcd_w, lcd_h, lcd_bits_dev,
-                                                                                       x_off, win_w, row_stride, x_off / 32);
+    if (old_kernel)
+      k_render_poses<<<(unsigned)((n + fpb - 1) / fpb), kRenderThreads, rsm_bytes, st>>>(h->scene_dev, poses_dev, variant_dev, n, lcd_w, lcd_h, lcd_bits_dev,
+                                                                                         x_off, win_w, row_stride, x_off / 32);
+    else
+      k_render_bodies<<<(unsigned)((n + kR2Frames - 1) / kR2Frames), kR2Threads, (size_t)kSceneBytes + sizeof(RowInk) * kR2Frames * (size_t)lcd_h, st>>>(
+          h->scene_dev, poses_dev, variant_dev, nullptr, 0, 0, n, lcd_w, lcd_h, lcd_bits_dev, x_off, win_w, row_stride, x_off / 32, 1, 0);
     CK(cudaGetLastError());
     h->launches += 1;
   }
@@ -1219,7 +1314,7 @@ int BLCD_P(scene_info)(BLCD_PENV* h, int32_t* out16) {
   if (!h || !out16) return fail("blcd_scene_info: bad arguments");
   const DScene& sc = h->scene;
   int32_t v[16] = {sc.nb, sc.nj, sc.nw, sc.np, sc.S, sc.P, sc.A, sc.lcd_w, sc.lcd_h, sc.maxm, sc.state_words, sc.hot_words, h->block,
-                   (int32_t)smem_bytes(h, h->block), BLCD_PROFILE_ID, 0};
+                   (int32_t)smem_bytes(h, h->block), BLCD_PROFILE_ID, h->pipeline};
   memcpy(out16, v, sizeof(v));
   return 0;
 }

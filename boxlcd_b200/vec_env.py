@@ -81,7 +81,7 @@ class VecWorldEnv:
     out = (C.c_int32 * 16)()
     _lib.check(self.l.blcd_scene_info(self.h, out))
     keys = ['n_bodies', 'n_joints', 'n_walls', 'n_pairs', 'obs_size', 'pobs_size', 'act_size', 'lcd_w', 'lcd_h', 'manifold_slots',
-            'state_words', 'smem_words_per_world', 'block', 'smem_bytes_per_block', 'profile']
+            'state_words', 'smem_words_per_world', 'block', 'smem_bytes_per_block', 'profile', 'pipeline']
     return dict(zip(keys, list(out)))
 
   @property

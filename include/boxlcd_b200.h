@@ -229,7 +229,8 @@ enum { BLCD_CNT_CONTACTS = 0, BLCD_CNT_POS_ITERS = 1, BLCD_CNT_TOI_EVENTS = 2, B
        BLCD_CNT_OVERFLOW = 5, BLCD_CNT_MANIFOLD_POINTS = 6, BLCD_CNT_SUBSTEPS = 7 };
 int blcd_get_counters(blcd_handle h, uint32_t* counters_dev, uint64_t stream);
 /* out16: n_bodies, n_joints, n_walls, n_pairs, obs_size, pobs_size, act_size, lcd_w, lcd_h, manifold slots per world,
- * state words per world, shared-memory words per world, threads per block, shared-memory bytes per block, 0, 0 */
+ * state words per world, shared-memory words per world, threads per block (fused kernels), shared-memory bytes per block,
+ * scene-size profile (0 small, 1 large), device path (0 fused one-thread-per-world kernel, 1 phase pipeline) */
 int blcd_scene_info(blcd_handle h, int32_t* out16);
 
 #ifdef __cplusplus
