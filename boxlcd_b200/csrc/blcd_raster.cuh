@@ -181,6 +181,153 @@ BLCD_HD RowMask polygon_row(const PolyPx& P, int y, int w, int h, int rules, int
   return mask;
 }
 
+// ---- the same scanline rules, written for converged warps ----------------------------------------------------------
+// polygon_row above walks data-dependent paths (insertion sort, early `continue`s, a division per crossing edge and row).
+// The render kernel gives every lane of a warp the same body, so the edge count is uniform: polygon_row_t<NE> unrolls the
+// edge loop, keeps the crossings in registers (slot 2i / 2i+1 of edge i, +inf when unused), sorts them with a fixed
+// merge-exchange network and takes the slopes from a per-body table (PolySlopes, one division per edge and BODY instead of
+// one per edge and ROW).  Same values, same spans: tests/test_hostsim_vs_oracle.py compares it with polygon_row on millions
+// of integer polygons, and the golden frames pin it on the GPU.
+struct PolySlopes { float dx[BLCD_MAX_VERTS]; };   // dx[i] = slope of edge P[i] -> P[i + 1 (mod n)], unused for horizontal edges
+
+BLCD_HD void polygon_slopes(PolySlopes& S, const PolyPx& P) {
+  for (int i = 0; i < BLCD_MAX_VERTS; ++i) {
+    const int j = (i + 1 < P.n && i + 1 < BLCD_MAX_VERTS) ? i + 1 : 0;
+    const int dy = P.y[j] - P.y[i];
+    S.dx[i] = (i < P.n && dy != 0) ? (float)(P.x[j] - P.x[i]) / (float)dy : 0.0f;
+  }
+}
+
+// exact integer forms of round_up_px / round_down_px for |f| < 2^23 (the fraction f - floor(f) is exact in fp32)
+BLCD_HD int round_up_px_i(float f) {
+  const float a = f >= 0.0f ? f : -f, fl = floorf(a);
+  const int r = (int)fl + ((a - fl) >= 0.5f ? 1 : 0);
+  return f >= 0.0f ? r : -r;
+}
+BLCD_HD int round_down_px_i(float f) {
+  const float a = f >= 0.0f ? f : -f, fl = floorf(a);
+  const int r = (int)fl + ((a - fl) > 0.5f ? 1 : 0);
+  return f >= 0.0f ? r : -r;
+}
+
+template <int NE>
+BLCD_HD RowMask polygon_row_t(const PolyPx& P, const PolySlopes& S, int y, int w, int h, int rules, int ylo, int yhi, int x_off) {
+  const int n = P.n;
+  if (n <= 0) return 0u;
+  int xl = P.x[0], yl = P.y[0];
+#pragma unroll
+  for (int i = 1; i < NE; ++i)
+    if (i == n - 1) { xl = P.x[i]; yl = P.y[i]; }
+  const int ne = (n > 1 && (xl != P.x[0] || yl != P.y[0])) ? n : n - 1;
+  if (ne <= 0) return 0u;
+  RowMask mask = 0u;
+  const int Ymin = ylo > 0 ? ylo : 0, Ymax = yhi < h ? yhi : h;
+  const bool in_range = (y >= Ymin && y <= Ymax);
+  const float INF = 3.0e38f;
+  float e[2 * NE];
+  int cnt = 0;
+#pragma unroll
+  for (int i = 0; i < NE; ++i) {
+    const bool last = (i + 1 >= n);
+    const int ex0 = P.x[i], ey0 = P.y[i];
+    const int ex1 = (last || i + 1 >= NE) ? P.x[0] : P.x[i + 1 < NE ? i + 1 : 0];
+    const int ey1 = (last || i + 1 >= NE) ? P.y[0] : P.y[i + 1 < NE ? i + 1 : 0];
+    const bool valid = i < ne;
+    const bool horizontal = ey0 == ey1;
+    if (valid && horizontal && ey0 == y && rules != BLCD_RASTER_PIL9) mask |= span_mask(ex0, ex1, w, x_off);
+    const int emin = ey0 < ey1 ? ey0 : ey1, emax = ey0 < ey1 ? ey1 : ey0;
+    const bool active = valid && !horizontal && in_range && emin <= y && y <= emax;
+    const bool twice = active && y == emax && y < Ymax;
+    const float xv = edge_x_at(ex0, ey0, S.dx[i], y);
+    e[2 * i] = active ? xv : INF;
+    e[2 * i + 1] = twice ? xv : INF;
+    cnt += (active ? 1 : 0) + (twice ? 1 : 0);
+  }
+  if (!in_range) return mask;
+  // Batcher's merge-exchange network over the 2 NE slots (compile-time index pairs: everything stays in registers)
+  constexpr int N = 2 * NE;
+#pragma unroll
+  for (int p = 1; p < N; p *= 2) {
+#pragma unroll
+    for (int k = p; k >= 1; k /= 2) {
+#pragma unroll
+      for (int j = k % p; j + k < N; j += 2 * k) {
+#pragma unroll
+        for (int i = 0; i < k; ++i) {
+          if (i + j + k < N && (i + j) / (2 * p) == (i + j + k) / (2 * p)) {
+            const float a = e[i + j], b = e[i + j + k];
+            e[i + j] = a < b ? a : b;
+            e[i + j + k] = a < b ? b : a;
+          }
+        }
+      }
+    }
+  }
+  if (rules == BLCD_RASTER_PIL9) {
+#pragma unroll
+    for (int k = 1; k < N; k += 2)
+      if (k < cnt) mask |= span_mask(round_up_px_i(e[k - 1]), round_down_px_i(e[k]), w, x_off);
+    return mask;
+  }
+  bool have_pos = false;
+  int pos = 0;
+#pragma unroll
+  for (int k = 1; k < N; k += 2) {
+    if (k < cnt) {
+      int xs = round_up_px_i(e[k - 1]);
+      const int xe = round_down_px_i(e[k]);
+      const bool skip = have_pos && xe < pos;
+      if (have_pos && xs < pos) xs = pos;
+      if (!skip && xe >= xs) {
+        mask |= span_mask(xs, xe, w, x_off);
+        pos = xe + 1; have_pos = true;
+      }
+    }
+  }
+  // apex extension (same tests as polygon_row; slopes from the table)
+#pragma unroll
+  for (int i = 1; i < NE; ++i) {
+    if (i >= ne) continue;
+    const bool ilast = (i + 1 >= n);
+    const int cx0 = P.x[i], cy0 = P.y[i];
+    const int cx1 = (ilast || i + 1 >= NE) ? P.x[0] : P.x[i + 1 < NE ? i + 1 : 0], cy1 = (ilast || i + 1 >= NE) ? P.y[0] : P.y[i + 1 < NE ? i + 1 : 0];
+    if (cy0 == cy1 || cx0 == cx1) continue;
+    const int cmin = cy0 < cy1 ? cy0 : cy1, cmax = cy0 < cy1 ? cy1 : cy0;
+    if (y != cmin && y != cmax) continue;
+    const int vx = (cy0 == y) ? cx0 : cx1;
+    const bool cpos = ((cx1 - cx0) > 0) == ((cy1 - cy0) > 0);
+#pragma unroll
+    for (int k = 0; k < i; ++k) {
+      const int ox0 = P.x[k], oy0 = P.y[k], ox1 = P.x[k + 1], oy1 = P.y[k + 1];   // k + 1 <= i < n: never the closing edge
+      if (oy0 == oy1 || ox0 == ox1) continue;
+      const bool opos = ((ox1 - ox0) > 0) == ((oy1 - oy0) > 0);
+      if (cpos != opos) continue;
+      const int omin = oy0 < oy1 ? oy0 : oy1, omax = oy0 < oy1 ? oy1 : oy0;
+      const bool top = (y == cmin && y == omin);
+      const bool bot = (y == cmax && y == omax && y == Ymax);
+      if (!top && !bot) continue;
+      const int ovx = (oy0 == y) ? ox0 : ox1;
+      if (vx != ovx) continue;
+      const int y2 = (y == Ymax) ? y - 1 : y + 1;
+      const float a1 = edge_x_at(cx0, cy0, S.dx[i], y2), a2 = edge_x_at(ox0, oy0, S.dx[k], y2);
+      if ((bot && cpos) || (top && !cpos)) {
+        const int s = round_up_px_i(BLCD_FADD(a1 > a2 ? a1 : a2, 1.0f));
+        if (s <= vx) mask |= span_mask(s, vx, w, x_off);
+      } else {
+        const int t = round_up_px_i(a1 < a2 ? a1 : a2) - 1;
+        if (t >= vx) mask |= span_mask(vx, t, w, x_off);
+      }
+    }
+  }
+  return mask;
+}
+
+BLCD_HD RowMask polygon_row_fast(const PolyPx& P, const PolySlopes& S, int y, int w, int h, int rules, int ylo, int yhi, int x_off = 0) {
+  // boxes and the luxo head (every limb of every robot): the unrolled 4-edge form.  Shapes with more vertices (one hull per crab /
+  // walker) take the general row function: unrolling 8 edges would double the kernel's registers for one body per frame.
+  return P.n <= 4 ? polygon_row_t<4>(P, S, y, w, h, rules, ylo, yhi, x_off) : polygon_row(P, y, w, h, rules, ylo, yhi, x_off);
+}
+
 // integer pixel vertices of a polygon fixture under transform (px, py, s, c)
 BLCD_HD void polygon_px(PolyPx& out, const DShape& sh, float px, float py, float s, float c, double world_w, double lcd_w) {
   out.n = sh.count;
@@ -234,6 +381,21 @@ BLCD_HD void body_px(BodyPx& o, const DShape& sh, float px, float py, float s, f
       if (i < o.P.n) { ylo = o.P.y[i] < ylo ? o.P.y[i] : ylo; yhi = o.P.y[i] > yhi ? o.P.y[i] : yhi; }
     o.y0 = ylo; o.y1 = yhi; o.x0 = 0; o.x1 = 0;
   }
+}
+
+// the converged-warp variant (k_render_bodies): slopes once per body, polygon_row_t
+struct BodyPxFast {
+  BodyPx b;
+  PolySlopes S;
+};
+BLCD_HD void body_px_fast(BodyPxFast& o, const DShape& sh, float px, float py, float s, float c, int world_w, int lcd_w) {
+  body_px(o.b, sh, px, py, s, c, world_w, lcd_w);
+  if (o.b.kind != SH_CIRCLE) polygon_slopes(o.S, o.b.P);
+}
+BLCD_HD RowMask body_px_row_fast(const BodyPxFast& o, int y, int win_w, int lcd_h, int rules, int x_off = 0) {
+  if (y < o.b.y0 || y > o.b.y1) return 0u;
+  if (o.b.kind == SH_CIRCLE) return ellipse_row(o.b.x0, o.b.y0, o.b.x1, o.b.y1, y, win_w, x_off);
+  return polygon_row_fast(o.b.P, o.S, y, win_w, lcd_h, rules, o.b.y0, o.b.y1, x_off);
 }
 
 // win_w / x_off: the column window whose ink is returned (the whole frame when it fits one RowMask)

@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(kRenderThreads) k_render_poses(const DScene* s
 // Poses come either from a pose array [n, nb, 4] (blcd_render_poses) or straight from the simulation state (the rollout
 // pipeline renders obs_t this way: frame w goes to output frame w * frame_mul + frame_add).
 constexpr int kR2Frames = 64, kR2Threads = 256;
-__global__ void __launch_bounds__(kR2Threads) k_render_bodies(const DScene* scene_g, const float* poses, const uint32_t* variants, const uint32_t* state, int64_t n_state,
+__global__ void __launch_bounds__(kR2Threads, 4) k_render_bodies(const DScene* scene_g, const float* poses, const uint32_t* variants, const uint32_t* state, int64_t n_state,
                                                               int64_t w_begin, int64_t n, int lcd_w, int lcd_h, uint32_t* bits, int x_off, int win_w, int row_stride, int word_off,
                                                               int64_t frame_mul, int64_t frame_add) {
   extern __shared__ __align__(16) unsigned char rsm[];
@@ -550,11 +550,11 @@ __global__ void __launch_bounds__(kR2Threads) k_render_bodies(const DScene* scen
       px = p[0]; py = p[1]; sn = p[2]; cs = p[3];
       variant = variants ? variants[i] : 0u;
     }
-    BodyPx bp;
-    body_px(bp, sc.body[b].shape[(variant >> b) & 1u], px, py, sn, cs, sc.world_w, lcd_w);
-    const int ylo = max(bp.y0, 0), yhi = min(bp.y1, lcd_h - 1);
+    BodyPxFast bp;
+    body_px_fast(bp, sc.body[b].shape[(variant >> b) & 1u], px, py, sn, cs, sc.world_w, lcd_w);
+    const int ylo = max(bp.b.y0, 0), yhi = min(bp.b.y1, lcd_h - 1);
     for (int y = ylo; y <= yhi; ++y) {
-      RowMask m = body_px_row(bp, y, win_w, lcd_h, sc.rules, x_off);
+      RowMask m = body_px_row_fast(bp, y, win_w, lcd_h, sc.rules, x_off);
       if (m) atomicOr(&rowink[f * lcd_h + y], (RowInk)m);
     }
   }

@@ -189,6 +189,41 @@ void hostsim_rollout(void* p, int T, float* full_state, uint32_t* bits, float* a
   }
 }
 
+// polygon_row_t (the converged-warp scanline rules of k_render_bodies) against polygon_row on random integer polygons:
+// convex hull-like quads, degenerate ones (collinear / repeated vertices after truncation), 3..8 vertices, rows inside and
+// outside, both rule sets, column windows.  Returns the number of mismatching (polygon, row) cases.
+int64_t hostsim_polygon_row_check(int64_t trials, uint64_t seed) {
+  uint64_t s = seed * 2654435761ull + 88172645463325252ull;
+  auto rnd = [&](int m) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (int)(s % (uint64_t)m); };
+  int64_t bad = 0;
+  for (int64_t t = 0; t < trials; ++t) {
+    PolyPx P;
+    const int kind = rnd(8);
+    P.n = kind < 5 ? 4 : 3 + rnd(6);
+    const int cx = rnd(40) - 4, cy = rnd(24) - 4, span = 1 + rnd(kind == 0 ? 3 : 12);
+    if (kind < 3) {            // rotated box-like quad: centre + two half-diagonals
+      int ax = rnd(2 * span + 1) - span, ay = rnd(2 * span + 1) - span, bx = -ay + rnd(3) - 1, by = ax + rnd(3) - 1;
+      if (kind == 2) { bx /= 3; by /= 3; }
+      int vx[4] = {cx - ax - bx, cx + ax - bx, cx + ax + bx, cx - ax + bx}, vy[4] = {cy - ay - by, cy + ay - by, cy + ay + by, cy - ay + by};
+      for (int i = 0; i < 4; ++i) { P.x[i] = vx[i]; P.y[i] = vy[i]; }
+    } else {
+      for (int i = 0; i < P.n; ++i) { P.x[i] = cx + rnd(2 * span + 1) - span; P.y[i] = cy + rnd(2 * span + 1) - span; }
+      if (rnd(4) == 0 && P.n > 1) { P.x[P.n - 1] = P.x[0]; P.y[P.n - 1] = P.y[0]; }
+    }
+    for (int i = P.n; i < BLCD_MAX_VERTS; ++i) { P.x[i] = 12345; P.y[i] = -777; }
+    int ylo = P.y[0], yhi = P.y[0];
+    for (int i = 1; i < P.n; ++i) { ylo = P.y[i] < ylo ? P.y[i] : ylo; yhi = P.y[i] > yhi ? P.y[i] : yhi; }
+    PolySlopes S;
+    polygon_slopes(S, P);
+    const int h = 8 + rnd(3) * 8, w = rnd(2) ? 32 : 24, rules = rnd(2), x_off = rnd(4) == 0 ? 8 * rnd(3) : 0;
+    for (int y = ylo - 1; y <= yhi + 1; ++y) {
+      RowMask a = polygon_row(P, y, w, h, rules, ylo, yhi, x_off), b = polygon_row_fast(P, S, y, w, h, rules, ylo, yhi, x_off);
+      bad += a != b;
+    }
+  }
+  return bad;
+}
+
 void hostsim_counters(void* p, uint32_t* out) {
   HostSim* h = (HostSim*)p;
   for (int64_t w = 0; w < h->n; ++w)

@@ -32,6 +32,8 @@ def lib(large=False):
     l.hostsim_observe.argtypes = [vp, vp, vp]
     l.hostsim_rollout.argtypes = [vp, C.c_int, vp, vp, vp]
     l.hostsim_step_pipeline.argtypes = [vp, vp, vp]
+    l.hostsim_polygon_row_check.argtypes = [i64, C.c_uint64]
+    l.hostsim_polygon_row_check.restype = i64
     l.hostsim_rollout_pipeline.argtypes = [vp, C.c_int, vp, vp, vp]
     l.hostsim_counters.argtypes = [vp, vp]
     l.hostsim_render_poses.argtypes = [vp, vp, vp, i64, C.c_int, C.c_int, vp]

@@ -142,3 +142,38 @@ def test_phase_pipeline_single_steps_and_mixing_with_the_fused_path(name):
     ow.step(act); hs.step(act, pipeline=(t % 2 == 0))
     assert (ow.get_bodies() == hs.get_bodies()).all(), t
   assert (ow.counters() == hs.counters()).all()
+
+
+@pytest.mark.parametrize('profile', ['small', 'large'])
+def test_converged_warp_scanline_rules_equal_the_row_rules(profile):
+  """csrc/blcd_raster.cuh: polygon_row_t (unrolled edges, sorting network, per-body slope table, integer rounding forms) --
+  what the render kernel runs -- against polygon_row (pinned to the reference through the golden frames) on 3 million random
+  integer polygons incl. degenerate ones, both Pillow rule sets, column windows, rows outside the polygon"""
+  from hostsim_py import lib
+  assert lib(large=(profile == 'large')).hostsim_polygon_row_check(3_000_000, 7) == 0
+
+
+@pytest.mark.parametrize('robot', ['quad', 'legs', 'walker', 'gingy', 'octo'])
+def test_robot_fillers_without_a_named_env_build_and_simulate(robot):
+  """world_defs.py:125-167, 251-368: robots the reference defines but never wires into a named env.  A custom WorldDef with each
+  must compile to a scene, reset, and step bit-for-bit like the oracle (small or large profile, whichever it needs), with
+  every hinge holding and nothing leaving the arena."""
+  from boxlcd_b200.world_env import WorldEnv
+  from boxlcd_b200.world_defs import WorldDef, Robot, Object
+  objects = [Object('object0', shape='box', size=0.4, density=0.5)] if robot in ('quad', 'walker') else []
+  env = WorldEnv(WorldDef(robots=[Robot(type=robot, name=f'{robot}0')], objects=objects), {'lcd_base': 32 if robot in ('gingy', 'octo', 'walker') else 16})
+  sp = env.layout.spec
+  assert sp.n_joints >= 2 and sp.n_bodies == sp.n_joints + 1 + len(objects)
+  assert env.act_size == sum(1 for j in range(sp.n_joints) if sp.joints[j].act_index >= 0) and env.obs_size == 4 * sp.n_bodies
+  n, T = 8, 25
+  ow, hs = oracle.OracleWorlds(sp, n, seed=3, threads=4), HostSim(sp, n, seed=3)
+  ow.reset(); hs.reset()
+  assert (ow.get_bodies() == hs.get_bodies()).all()
+  ro, rh = ow.rollout(T), hs.rollout(T)
+  for k in ro:
+    assert (ro[k] == rh[k]).all(), k
+  rp = HostSim(sp, n, seed=3); rp.reset()
+  assert (rp.rollout(T, pipeline=True)['full_state'] == ro['full_state']).all()
+  b = ow.get_bodies()
+  assert np.isfinite(b).all() and b[..., 1].min() > -0.2 and b[..., 0].min() > -0.2 and b[..., 0].max() < env.WIDTH + 0.2
+  assert (~oracle.unpack_bits(ro['lcd_bits'], sp.lcd_w)).sum((2, 3)).min() >= 8      # the robot is on the frame
