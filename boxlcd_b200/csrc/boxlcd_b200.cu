@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(kPipeBlock, kVelBlocks) k_pipe_vel(const DScen
 // converged writes it back and fetches the next unprocessed world from a global counter.  Everything a sweep needs is in
 // the lane's own shared-memory column / local records, filled from the scratch area, so any lane can take any world.
 __global__ void __launch_bounds__(kPipeBlock, kPosBlocks) k_pipe_pos(const DScene* scene_g, uint32_t* state, uint32_t* scratch, int64_t n, int64_t w_begin, int64_t w_end,
-                                                                     unsigned long long* next, int refill, const uint32_t* bin_count, const uint32_t* bin_list) {
+                                                                     unsigned long long* next, int refill, const uint32_t* bin_count, const uint32_t* bin_list, int sort_mode) {
   unsigned char* smem_raw = blcd_smem;
   const DScene& sc = stage_scene<kPipeBlock>(scene_g, smem_raw);
   Sim<kPipeBlock> sim(sc, hot_base<kPipeBlock>(smem_raw), state, n, w_begin);
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kPipeBlock, kPosBlocks) k_pipe_pos(const DScen
         long long idx = (long long)atomicAdd(next, 1ull);
         if (idx >= count) { exhausted = true; break; }
         int64_t w = w_begin + idx;
-        if (bin_list) {   // position idx of the longest-first order
+        if (bin_list && sort_mode == 1) {   // position idx of the longest-first order (sweeps needed last time)
           int key = kPosBins - 1;
           for (; key > 0; --key) {
             const long long c = (long long)bin_count[kVelBins + key];
@@ -367,6 +367,14 @@ __global__ void __launch_bounds__(kPipeBlock, kPosBlocks) k_pipe_pos(const DScen
             idx -= c;
           }
           w = w_begin + (int64_t)bin_list[(int64_t)(kVelBins + key) * n + w_begin + idx];
+        } else if (bin_list) {              // the velocity kernel's order: worlds with the same number of contacts arrive together
+          int key = kVelBins - 1;
+          for (; key > 0; --key) {
+            const long long c = (long long)bin_count[key];
+            if (idx < c) break;
+            idx -= c;
+          }
+          w = w_begin + (int64_t)bin_list[(int64_t)key * n + w_begin + idx];
         }
         sim.g.p = state + w;
         sim.attach_scratch(scratch, w);
@@ -603,6 +611,7 @@ struct BLCD_PENV {
   uint32_t* bin_count = nullptr;    // [kHostStreams][kVelBins] worlds per velocity-sort key in the current sub-step
   uint32_t* bin_list = nullptr;     // [kVelBins][n] range-relative world indices filed under each key
   int sm_count = 148;
+  uint64_t dbg_toi_worlds = 0, dbg_toi_total = 0;
   cudaStream_t pstream[kHostStreams] = {};   // world ranges of one pipeline call run on streams of their own
   cudaEvent_t pev[kHostStreams] = {}, pev_begin = nullptr;
 };
@@ -784,6 +793,7 @@ int BLCD_P(rekey)(BLCD_PENV* h, uint64_t seed, int64_t world_offset) {
 int BLCD_P(destroy)(BLCD_PENV* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
+  if (h->dbg_toi_total) fprintf(stderr, "[blcd] worlds reaching the TOI kernel: %.4f of world-sub-steps\n", (double)h->dbg_toi_worlds / (double)h->dbg_toi_total);
   for (auto& st : h->hstream) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }   // nothing in flight past here
   cudaFree(h->scene_dev);
   cudaFree(h->state);
@@ -912,7 +922,7 @@ static void pipeline_substep(BLCD_PENV* h, const float* actions_dev, int mode, i
   static const int pos_resident = getenv("BLCD_POS_BLOCKS") ? atoi(getenv("BLCD_POS_BLOCKS")) : kPosBlocks;
   unsigned pos_blocks = (unsigned)(h->sm_count * (pos_resident < 1 ? 1 : (pos_resident > kPosBlocks ? kPosBlocks : pos_resident)));
   if (pos_blocks > blocks) pos_blocks = blocks;
-  static const bool pos_sort = !(getenv("BLCD_POS_SORT") && atoi(getenv("BLCD_POS_SORT")) == 0);
+  static const int pos_sort = getenv("BLCD_POS_SORT") ? atoi(getenv("BLCD_POS_SORT")) : 2;   // 0 world order, 1 by previous sweep count, 2 by contact count
   static const int pos_refill = getenv("BLCD_POS_REFILL") ? atoi(getenv("BLCD_POS_REFILL")) : 16;
   {
     {
@@ -935,8 +945,15 @@ static void pipeline_substep(BLCD_PENV* h, const float* actions_dev, int mode, i
                                                  w0, w1, cnt, h->pos_next + slot, bins, h->bin_list);
       static const bool vel_sort = !(getenv("BLCD_VEL_SORT") && atoi(getenv("BLCD_VEL_SORT")) == 0);
       k_pipe_vel<<<blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, w0, w1, bins, vel_sort ? h->bin_list : nullptr);
-      k_pipe_pos<<<pos_blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, w0, w1, h->pos_next + slot, pos_refill, bins, pos_sort ? h->bin_list : nullptr);
+      k_pipe_pos<<<pos_blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, w0, w1, h->pos_next + slot, pos_refill, bins, pos_sort ? h->bin_list : nullptr, pos_sort);
       k_pipe_post<<<blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, h->seed, h->world_offset, w0, w1, cnt, list, bins);
+      static const bool dbg_toi = getenv("BLCD_DEBUG_TOI") != nullptr;   // diagnostic: share of worlds that reach the TOI kernel
+      if (dbg_toi) {
+        uint32_t c = 0;
+        cudaMemcpyAsync(&c, cnt, 4, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        h->dbg_toi_worlds += c; h->dbg_toi_total += (uint64_t)(w1 - w0);
+      }
       k_pipe_toi<<<blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, h->seed, h->world_offset, w0, cnt, list);
       h->launches += 5;
     }
@@ -1160,7 +1177,12 @@ static int host_chunks_default(BLCD_PENV* h) {
   if (h->host_chunks_env > 0) return h->host_chunks_env;
   if (h->timing) return 1;
   if (h->pipeline) return h->n >= 4 * 98304 ? 4 : (h->n >= 2 * 98304 ? 2 : 1);   // every range must still fill the GPU phase by phase
-  return kHostStreams;
+  // fused kernel: one block per SM, so a handle of at most one wave of blocks is stepped as ONE range (splitting it would round
+  // every range up to whole blocks and spill into a second wave: 32 768 worlds in 8 ranges are 152 blocks of 224 on 148 SMs);
+  // larger handles overlap the copies of one range with the kernel of the next
+  const int64_t blocks = (h->n + h->block - 1) / h->block;
+  if (blocks <= h->sm_count) return 1;
+  return blocks <= 2 * (int64_t)h->sm_count ? 2 : kHostStreams;
 }
 
 int BLCD_P(step_host)(BLCD_PENV* h, const float* actions_host, float* full_state_host, uint32_t* lcd_bits_host, uint8_t* done_host) {

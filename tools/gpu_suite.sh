@@ -1,10 +1,18 @@
-mkdir -p gpurun_out/r02k
-python -m pytest tests -m gpu -q > gpurun_out/r02k/pytest_gpu.log 2>&1; tail -12 gpurun_out/r02k/pytest_gpu.log
-BLCD_PIPELINE=1 python -m pytest tests -m gpu -q > gpurun_out/r02k/pytest_gpu_pipeline.log 2>&1; tail -8 gpurun_out/r02k/pytest_gpu_pipeline.log
-python tools/pipe_time.py Urchin 262144 20 2>&1 | tail -1
-python bench.py --steps 2 --warmup 3 > gpurun_out/r02k/bench.json 2> gpurun_out/r02k/bench.err; tail -3 gpurun_out/r02k/bench.err
+# one-GPU evidence run: GPU test suite (auto path and forced pipeline), headline bench, per-env benches, ncu launch list
+OUT=gpurun_out/r02p
+mkdir -p $OUT
+python -m pytest tests -m gpu -q -rA > $OUT/pytest_gpu.log 2>&1; tail -3 $OUT/pytest_gpu.log
+BLCD_PIPELINE=1 python -m pytest tests -m gpu -q > $OUT/pytest_gpu_pipeline.log 2>&1; tail -2 $OUT/pytest_gpu_pipeline.log
+python bench.py --steps 3 --warmup 3 > $OUT/bench_1gpu.json 2> $OUT/bench.err; tail -2 $OUT/bench.err
+for e in Dropbox Bounce2 UrchinBall LuxoCube; do w=262144; if [ $e = Bounce2 ]; then w=65536; fi; if [ $e = Dropbox ]; then w=10000; fi; python bench.py --env $e --worlds $w --steps 2 --warmup 3 --no_ncu --no_render --cpu_seconds 6 > $OUT/bench_$e.json 2>> $OUT/bench.err; done
+python bench.py --env Bounce2 --worlds 262144 --steps 2 --warmup 3 --no_ncu --no_render --no_cpu > $OUT/bench_Bounce2_262144.json 2>> $OUT/bench.err
+python bench.py --env CrabCube --worlds 65536 --steps 2 --warmup 2 --no_ncu --no_render --no_cpu --no_e2e > $OUT/bench_CrabCube.json 2>> $OUT/bench.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 3 --no_cpu --no_e2e --no_ncu --T 10 > $OUT/ncu_bench.log 2>&1; tail -1 $OUT/ncu_bench.log | cut -c1-200
 python - <<PY
-import json
-d=json.load(open("gpurun_out/r02k/bench.json"))
-print({k:d[k] for k in ["value","ms_per_step","gpu_launches"]}, d["e2e"]["value"], d["e2e"]["pipelined_value"], d["roofline_solver"].get("frac"), d["roofline_solver"].get("counters",{}).get("active_lanes_per_warp_inst"), d["roofline"]["traffic"], d["render_roofline"])
+import json, glob
+for f in sorted(glob.glob("$OUT/bench_*.json")):
+  try:
+    d = [json.loads(l) for l in open(f) if l.startswith("{")][-1]
+    print(f.split("/")[-1], round(d["value"] / 1e6, 2), "M; e2e", d["e2e"] and round(d["e2e"]["value"] / 1e6, 2), "cpu", d.get("cpu_baseline") and round(d["cpu_baseline"]["value"] / 1e6, 3), d["config"]["scene"]["block"], d["config"]["scene"].get("pipeline"), d.get("roofline_solver", {}).get("frac"))
+  except Exception as e: print(f, "failed", e)
 PY
