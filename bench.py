@@ -198,7 +198,8 @@ def ncu_instruction_count(env_name, n, T, pipeline, timeout=300):
   """Count, IN THIS RUN, the instructions of one rollout: an `ncu --metrics` sub-process profiles every kernel this library
   launches for one T-step rollout of n worlds (tools/ncu_case.py brackets it with cudaProfilerStart/Stop) and the
   per-kernel counters are summed.  Returns None when ncu is unavailable (then nothing is reported -- no static copy)."""
-  metrics = 'smsp__inst_executed.sum,smsp__thread_inst_executed.sum,sm__inst_executed_pipe_fma.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum'
+  metrics = ('smsp__inst_executed.sum,smsp__thread_inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,'
+             'dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum')
   cmd = ['ncu', '--csv', '--profile-from-start', 'off', '--clock-control', 'none', '--metrics', metrics,
          sys.executable, os.path.join(ROOT, 'tools', 'ncu_case.py'), env_name, str(n), str(T), 'range']
   try:
@@ -210,20 +211,36 @@ def ncu_instruction_count(env_name, n, T, pipeline, timeout=300):
   start = text.find('"ID"')
   if res.returncode != 0 or start < 0:
     return {'unavailable': (res.stderr or res.stdout)[-300:].replace('\n', ' ')}
-  tot, kernels = {}, {}
+  tot, kernels, launches = {}, {}, {}
   for row in csv.DictReader(io.StringIO(text[start:])):
     try:
       val = float(row['Metric Value'].replace(',', ''))
     except Exception:
       continue
     unit = row.get('Metric Unit', '')
+    k = row['Kernel Name'].split('(')[0].split('::')[-1]
     if row['Metric Name'] == 'gpu__time_duration.sum':
       val *= {'ns': 1e-9, 'us': 1e-6, 'ms': 1e-3, 's': 1.0}.get(unit, 1e-9)
-      k = row['Kernel Name'].split('(')[0]
       kernels[k] = kernels.get(k, 0.0) + val
     if row['Metric Name'].startswith('dram__bytes'):
       val *= {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(unit, 1)
-    tot[row['Metric Name']] = tot.get(row['Metric Name'], 0.0) + val
+    launches.setdefault((row['ID'], k), {})[row['Metric Name']] = val
+    if not row['Metric Name'].startswith('smsp__issue_active'):
+      tot[row['Metric Name']] = tot.get(row['Metric Name'], 0.0) + val
+  # per kernel: share of the GPU time, lanes per instruction, issue-slot utilisation (duration-weighted over its launches)
+  per_kernel = {}
+  for (_, k), m in launches.items():
+    a = per_kernel.setdefault(k, {'seconds': 0.0, 'warp_inst': 0.0, 'lane_inst': 0.0, 'issue_x_s': 0.0, 'launches': 0})
+    dur = m.get('gpu__time_duration.sum', 0.0)
+    a['seconds'] += dur; a['launches'] += 1
+    a['warp_inst'] += m.get('smsp__inst_executed.sum', 0.0); a['lane_inst'] += m.get('smsp__thread_inst_executed.sum', 0.0)
+    a['issue_x_s'] += m.get('smsp__issue_active.avg.pct_of_peak_sustained_active', 0.0) * dur
+  all_s = max(sum(a['seconds'] for a in per_kernel.values()), 1e-12)
+  for k, a in per_kernel.items():
+    a['share_of_gpu_time'] = a['seconds'] / all_s
+    a['active_lanes_per_warp_inst'] = a['lane_inst'] / max(a['warp_inst'], 1.0)
+    a['issue_slot_utilisation_pct'] = a.pop('issue_x_s') / max(a['seconds'], 1e-12)
+    a['frac_of_lane_issue_peak'] = a['issue_slot_utilisation_pct'] / 100.0 * a['active_lanes_per_warp_inst'] / 32.0
   if 'smsp__thread_inst_executed.sum' not in tot:
     return {'unavailable': 'ncu printed no counters'}
   steps = float(n) * T
@@ -231,8 +248,7 @@ def ncu_instruction_count(env_name, n, T, pipeline, timeout=300):
           'warp_inst_per_env_step': tot['smsp__inst_executed.sum'] / steps,
           'active_lanes_per_warp_inst': tot['smsp__thread_inst_executed.sum'] / max(tot['smsp__inst_executed.sum'], 1.0),
           'dram_bytes_per_env_step': (tot.get('dram__bytes_read.sum', 0.0) + tot.get('dram__bytes_write.sum', 0.0)) / steps,
-          'kernel_seconds_under_ncu': {k: v for k, v in sorted(kernels.items(), key=lambda kv: -kv[1])[:8]},
-          'kernel_share_of_gpu_time_under_ncu': {k: v / max(sum(kernels.values()), 1e-12) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1])[:8]},
+          'per_kernel_under_ncu': dict(sorted(per_kernel.items(), key=lambda kv: -kv[1]['seconds'])[:8]),
           'source': 'ncu sub-process of this bench run (cold caches, serialised kernels): counts, not times, are used'}
 
 
@@ -408,7 +424,7 @@ def main():
     r_ms = r0.elapsed_time(r1) / 5
     frame_words = int(np.prod(v.bits_shape()))
     r_bytes = nr * (16 * v.B + 4 * frame_words)
-    render = {'kernel': 'k_render_poses', 'frames': nr, 'ms': r_ms, 'frames_per_s': nr / (r_ms / 1e3), 'algorithmic_bytes_per_frame': 16 * v.B + 4 * frame_words,
+    render = {'kernel': 'k_render_bodies', 'frames': nr, 'ms': r_ms, 'frames_per_s': nr / (r_ms / 1e3), 'algorithmic_bytes_per_frame': 16 * v.B + 4 * frame_words,
               'achieved_gbs': r_bytes / (r_ms / 1e3) / 1e9}
     del poses
   if rank != 0:
@@ -446,6 +462,10 @@ def main():
   if counts and 'lane_inst_per_env_step' in counts:
     solver.update(achieved=counts['lane_inst_per_env_step'] * per_gpu_rate, frac=counts['lane_inst_per_env_step'] * per_gpu_rate / lane_peak,
                   issue_slot_utilisation=counts['warp_inst_per_env_step'] * per_gpu_rate * 32 / lane_peak, counters=counts)
+    top = next(iter(counts['per_kernel_under_ncu'].items()), None)
+    if top:
+      solver['dominant_kernel'] = dict(top[1], name=top[0], note='share, lanes and issue-slot utilisation of the kernel with the largest share of the GPU time '
+                                       '(ncu sub-process of this run); frac_of_lane_issue_peak = issue utilisation x active lanes / 32')
   else:
     solver.update(achieved=None, frac=None, counters=counts)
   if per_sub is not None:
