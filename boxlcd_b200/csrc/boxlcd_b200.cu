@@ -261,7 +261,6 @@ __global__ void __launch_bounds__(BLOCK) k_observe(const DScene* scene_g, uint32
 constexpr int kPipeBlock = 128;
 // resident blocks per SM each phase kernel is compiled for (register cap = 65536 / (128 x blocks)) and given shared memory for
 constexpr int kPreBlocks = 4, kVelBlocks = 4, kPosBlocks = 4, kPostBlocks = 4;
-constexpr int kPipeCarveBlocks = 4;   // every phase kernel asks for the same shared-memory carve-out, so kernels of different world ranges can share an SM
 // The velocity kernel takes its worlds in SORTED order: k_pipe_pre files every world under the key (touching contacts, how
 // many of them have two points), k_pipe_vel walks the bins from the busiest key down.  A warp then holds 32 worlds with the
 // same contact count, so the contact part of a velocity sweep runs with full warps instead of the warp's busiest lane
@@ -902,8 +901,10 @@ static int pipeline_prepare(BLCD_PENV* h) {
   CK(cudaMalloc(&h->pos_next, kHostStreams * sizeof(unsigned long long)));
   CK(cudaMemset(h->pos_next, 0, kHostStreams * sizeof(unsigned long long)));
   const size_t sb = smem_bytes(h, kPipeBlock);
-  if (set_smem_attr(k_pipe_pre, sb, kPipeCarveBlocks) || set_smem_attr(k_pipe_vel, sb, kPipeCarveBlocks) || set_smem_attr(k_pipe_pos, sb, kPipeCarveBlocks) ||
-      set_smem_attr(k_pipe_post, sb, kPipeCarveBlocks) || set_smem_attr(k_pipe_toi, sb, kPipeCarveBlocks))
+  // shared memory for the blocks each kernel is compiled to keep resident; the rest of the SM's array is L1, which the
+  // velocity / position kernels need for their thread-local contact records
+  if (set_smem_attr(k_pipe_pre, sb, kPreBlocks) || set_smem_attr(k_pipe_vel, sb, kVelBlocks) || set_smem_attr(k_pipe_pos, sb, kPosBlocks) ||
+      set_smem_attr(k_pipe_post, sb, kPostBlocks) || set_smem_attr(k_pipe_toi, smem_bytes(h, kToiBlock), 16))
     return -1;
   for (int r = 0; r < kHostStreams; ++r) {
     if (!h->pstream[r]) CK(cudaStreamCreateWithFlags(&h->pstream[r], cudaStreamNonBlocking));
