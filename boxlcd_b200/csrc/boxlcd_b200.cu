@@ -271,6 +271,17 @@ constexpr int kVelBinsC = 8, kVelBinsP = 4, kVelBins = kVelBinsC * kVelBinsP;
 // need about as many sweeps as in its previous sub-step, so worlds are also filed by that count (kPosBins bins of 4 sweeps) and
 // fetched from the top bin down -- the stragglers start early and the cheap worlds fill the tail of the launch.
 constexpr int kPosBins = 16, kAllBins = kVelBins + kPosBins;
+// atomicAdd(counter + key, 1) for every calling lane, aggregated per warp: lanes with the same key elect a leader that adds the
+// group size once; each lane gets its own slot.  (One atomic per world on a handful of hot addresses serialises at L2.)
+__device__ __forceinline__ uint32_t warp_agg_inc(uint32_t* counters, int key) {
+  const unsigned peers = __match_any_sync(__activemask(), key);
+  const int leader = __ffs(peers) - 1, lane = (int)(threadIdx.x & 31u);
+  uint32_t base = 0u;
+  if (lane == leader) base = atomicAdd(counters + key, (uint32_t)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  return base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+}
+
 __device__ __forceinline__ int vel_bin_key(int nc, int n2) {
   return (nc < kVelBinsC ? nc : kVelBinsC - 1) * kVelBinsP + (n2 < kVelBinsP ? n2 : kVelBinsP - 1);
 }
@@ -279,7 +290,7 @@ __device__ __forceinline__ int vel_bin_key(int nc, int n2) {
 __global__ void __launch_bounds__(kPipeBlock, kPreBlocks) k_pipe_pre(const DScene* scene_g, uint32_t* state, uint32_t* scratch, int64_t n, uint64_t seed, int64_t world_offset,
                                                             const float* actions, int mode, int T, int t, int first, OutPtrs out,
                                                             int64_t w_begin, int64_t w_end, uint32_t* toi_count, unsigned long long* pos_next,
-                                                            uint32_t* bin_count, uint32_t* bin_list) {
+                                                            uint32_t* bin_count, uint32_t* bin_list, int file_prev) {
   unsigned char* smem_raw = blcd_smem;
   const DScene& sc = stage_scene<kPipeBlock>(scene_g, smem_raw);
   if (blockIdx.x == 0 && threadIdx.x == 0) { *toi_count = 0u; *pos_next = 0ull; }   // this sub-step's TOI list and position work counter start empty
@@ -307,10 +318,12 @@ __global__ void __launch_bounds__(kPipeBlock, kPreBlocks) k_pipe_pre(const DScen
   int n2 = 0;
   for (int k = 0; k < sim.nc; ++k) n2 += ((sim.cru(kHotCon * k + C_PK) >> 10) & 3u) == 2u;
   const int key = vel_bin_key(sim.nc, n2);
-  bin_list[(int64_t)key * n + w_begin + atomicAdd(bin_count + key, 1u)] = (uint32_t)(w - w_begin);
-  const uint32_t prev = sim.x.u(pipe_prev_sweeps_word(sc));
-  const int pkey = kVelBins + (int)(prev / 4u < (uint32_t)kPosBins ? prev / 4u : (uint32_t)kPosBins - 1u);
-  bin_list[(int64_t)pkey * n + w_begin + atomicAdd(bin_count + pkey, 1u)] = (uint32_t)(w - w_begin);
+  bin_list[(int64_t)key * n + w_begin + warp_agg_inc(bin_count, key)] = (uint32_t)(w - w_begin);
+  if (file_prev) {   // the longest-first order of the position kernel (BLCD_POS_SORT=1): by the sweeps needed last time
+    const uint32_t prev = sim.x.u(pipe_prev_sweeps_word(sc));
+    const int pkey = kVelBins + (int)(prev / 4u < (uint32_t)kPosBins ? prev / 4u : (uint32_t)kPosBins - 1u);
+    bin_list[(int64_t)pkey * n + w_begin + warp_agg_inc(bin_count, pkey)] = (uint32_t)(w - w_begin);
+  }
 }
 
 __global__ void __launch_bounds__(kPipeBlock, kVelBlocks) k_pipe_vel(const DScene* scene_g, uint32_t* state, uint32_t* scratch, int64_t n, int64_t w_begin, int64_t w_end,
@@ -355,7 +368,13 @@ __global__ void __launch_bounds__(kPipeBlock, kPosBlocks) k_pipe_pos(const DScen
     const unsigned idle = __ballot_sync(0xFFFFFFFFu, !have && !exhausted);
     if (idle && (__popc(idle) >= refill || !__any_sync(0xFFFFFFFFu, have))) {
       while (!have && !exhausted) {
-        long long idx = (long long)atomicAdd(next, 1ull);
+        // one atomic per warp and round: the fetching lanes take consecutive indices
+        const unsigned takers = __activemask();
+        const int lane = (int)(threadIdx.x & 31u), leader = __ffs(takers) - 1;
+        unsigned long long base = 0ull;
+        if (lane == leader) base = atomicAdd(next, (unsigned long long)__popc(takers));
+        base = __shfl_sync(takers, base, leader);
+        long long idx = (long long)base + __popc(takers & ((1u << lane) - 1u));
         if (idx >= count) { exhausted = true; break; }
         int64_t w = w_begin + idx;
         if (bin_list && sort_mode == 1) {   // position idx of the longest-first order (sweeps needed last time)
@@ -405,7 +424,7 @@ __global__ void __launch_bounds__(kPipeBlock, kPostBlocks) k_pipe_post(const DSc
   Sim<kPipeBlock> sim(sc, hot_base<kPipeBlock>(smem_raw), state, n, w, w_end);
   sim.attach_scratch(scratch, w);
   sim.load(seed, world_offset + w);
-  if (pipe_post(sim)) toi_list[atomicAdd(toi_count, 1u)] = (uint32_t)(w - w_begin);
+  if (pipe_post(sim)) toi_list[warp_agg_inc(toi_count, 0)] = (uint32_t)(w - w_begin);
 }
 
 // One warp per block: a world's SolveTOI takes anything from one pre-filtered scan to eight events, and a block holds its
@@ -948,7 +967,7 @@ static void pipeline_substep(BLCD_PENV* h, const float* actions_dev, int mode, i
         out.lcd_bits = nullptr;
       }
       k_pipe_pre<<<blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, h->seed, h->world_offset, actions_dev, mode, T, t, s == 0 ? 1 : 0, out,
-                                                 w0, w1, cnt, h->pos_next + slot, bins, h->bin_list);
+                                                 w0, w1, cnt, h->pos_next + slot, bins, h->bin_list, pos_sort == 1);
       static const bool vel_sort = !(getenv("BLCD_VEL_SORT") && atoi(getenv("BLCD_VEL_SORT")) == 0);
       k_pipe_vel<<<blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, w0, w1, bins, vel_sort ? h->bin_list : nullptr);
       k_pipe_pos<<<pos_blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, w0, w1, h->pos_next + slot, pos_refill, bins, pos_sort ? h->bin_list : nullptr, pos_sort);
