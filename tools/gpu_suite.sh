@@ -7,7 +7,6 @@ python bench.py --steps 3 --warmup 3 > $OUT/bench_1gpu.json 2> $OUT/bench.err; t
 for e in Dropbox Bounce2 UrchinBall LuxoCube; do w=262144; if [ $e = Bounce2 ]; then w=65536; fi; if [ $e = Dropbox ]; then w=10000; fi; python bench.py --env $e --worlds $w --steps 2 --warmup 3 --no_ncu --no_render --cpu_seconds 6 > $OUT/bench_$e.json 2>> $OUT/bench.err; done
 python bench.py --env Bounce2 --worlds 262144 --steps 2 --warmup 3 --no_ncu --no_render --no_cpu > $OUT/bench_Bounce2_262144.json 2>> $OUT/bench.err
 python bench.py --env CrabCube --worlds 65536 --steps 2 --warmup 2 --no_ncu --no_render --no_cpu --no_e2e > $OUT/bench_CrabCube.json 2>> $OUT/bench.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 3 --no_cpu --no_e2e --no_ncu --T 10 > $OUT/ncu_bench.log 2>&1; tail -1 $OUT/ncu_bench.log | cut -c1-200
 python - <<PY
 import json, glob
 for f in sorted(glob.glob("$OUT/bench_*.json")):
