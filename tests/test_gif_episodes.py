@@ -193,6 +193,11 @@ def test_cuda_path_tracks_recorded_robot_episode(name):
   K, min_exact, max_px = ROBOT_GIFS[name]
   track = int(np.argmax(d > 12)) if (d > 12).any() else len(d)
   print(f'{name}: CUDA path {int((d == 0).sum())} of {len(d)} frames bit-exact; within 12 px of the recording for the first {track} frames')
-  # sincosf / FMA last-bit differences are amplified by every impact of these chaotic episodes, so the CUDA path is only
-  # required to stay on the recording for the opening third; the oracle test above covers the full length
-  assert track >= K // 3 and (d[:K // 3] == 0).sum() >= 0.8 * (K // 3)
+  # The CUDA path differs from the oracle by sincosf / FMA last bits, i.e. it is one more one-ulp-perturbed copy of it: over
+  # the FULL episode it must stay on the recording up to (three quarters of) the frame at which one-ulp copies of the oracle
+  # itself leave the oracle (tests/test_gif_hires.py: chaos_horizon), and be bit-exact on most frames until then.
+  # Measured on a B200: on the recording for 68 / 79 / 147 / 94 / 92 frames (Urchin / Luxo / UrchinCube / UrchinBall / LuxoBall).
+  from test_gif_hires import chaos_horizon
+  need = min(K, int(chaos_horizon(name).min())) * 3 // 4
+  print(f'{name}: required {need} frames (one-ulp chaos horizon of the oracle: {int(chaos_horizon(name).min())})')
+  assert track >= need and (d[:need] == 0).sum() >= 0.7 * need
