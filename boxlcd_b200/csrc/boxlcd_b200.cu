@@ -731,9 +731,13 @@ int BLCD_P(create)(const blcd_spec* spec_host, int64_t n_worlds, int device, uin
 #else
     h->block = 128;
 #endif
-  } else if (h->scene.nj == 0) {
+  } else if (h->scene.nj == 0 || BLCD_PROFILE_ID == 0) {
+    // relative time of one block by size: joint-free scenes grow slowly; articulated ones almost in proportion (their joint
+    // records spill above 256 threads), so a larger block only pays when it saves a whole wave -- 65 536 Urchin worlds are
+    // 1.73 waves of 256-thread blocks but ONE wave of 448 (measured 15.7 M env-steps/s against 14.2 M; LuxoCube 9.4 against 8.7)
     const int sizes[] = {256, 320, 384, 448, 512};
-    const double rel[] = {1.00, 1.09, 1.175, 1.26, 1.35};
+    const double rel_free[] = {1.00, 1.09, 1.175, 1.26, 1.35}, rel_joint[] = {1.00, 1.27, 1.43, 1.81, 1.91};
+    const double* rel = h->scene.nj == 0 ? rel_free : rel_joint;
     double best = 0.0;
     for (int i = 0; i < 5; ++i) {
       if (smem_bytes(h, sizes[i]) > (size_t)smem_max) continue;
