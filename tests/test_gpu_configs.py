@@ -286,7 +286,7 @@ def test_results_do_not_depend_on_the_block_size(name, monkeypatch):
   env = make_env(name)
   n, T = 3000, 25
   outs = []
-  for block in ('128', '256', '320', '384', '448', '512'):
+  for block in ('128', '160', '224', '256', '320', '384', '448', '512'):
     monkeypatch.setenv('BLCD_BLOCK', block)
     v = vec(env, n, seed=9)
     assert v.info()['block'] == int(block)
@@ -299,7 +299,11 @@ def test_results_do_not_depend_on_the_block_size(name, monkeypatch):
     for a, b in zip(outs[0], o):
       assert (a == b).all()
   monkeypatch.delenv('BLCD_BLOCK')
-  assert vec(make_env('Bounce2'), 65536).info()['block'] == 448 and vec(make_env('Urchin'), 65536).info()['block'] == 256
+  # wave-aware choices: 65 536 worlds are one wave of 448-thread blocks (also for articulated scenes, since round 2); 32 768
+  # worlds (262 144 over 8 GPUs) one wave of 224-thread blocks; large batches go to the phase pipeline
+  assert vec(make_env('Bounce2'), 65536).info()['block'] == 448 and vec(make_env('Urchin'), 65536).info()['block'] == 448
+  assert vec(make_env('Urchin'), 32768).info()['block'] == 224 and vec(make_env('Urchin'), 32768).info()['pipeline'] == 0
+  assert vec(make_env('Urchin'), 131072).info()['pipeline'] == 1
 
 
 def test_rekeyed_handle_equals_a_fresh_one_and_splits_differ(tmp_path):
