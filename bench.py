@@ -204,7 +204,8 @@ def ncu_instruction_count(env_name, n, T, pipeline, timeout=300):
          sys.executable, os.path.join(ROOT, 'tools', 'ncu_case.py'), env_name, str(n), str(T), 'range']
   try:
     # the sub-process must take the same device path as the timed handle (the library picks it from the world count)
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=dict(os.environ, BLCD_PIPELINE=str(int(pipeline))))
+    # ... and one world range per launch: under ncu the kernels are serialised anyway, and every launch then covers all worlds
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=dict(os.environ, BLCD_PIPELINE=str(int(pipeline)), BLCD_PIPE_RANGES='1'))
   except Exception as e:
     return {'unavailable': f'{type(e).__name__}: {e}'[:200]}
   text = res.stdout
@@ -452,7 +453,7 @@ def main():
   counts = None
   if not a.no_ncu:
     torch.cuda.synchronize()
-    counts = ncu_instruction_count(a.env, min(n, 131072), 2, info.get('pipeline', 0))
+    counts = ncu_instruction_count(a.env, n, 1 if info.get('pipeline', 0) else 3, info.get('pipeline', 0))
   per_gpu_rate = n * T / (k_ms / 1e3)      # env-steps/s of this GPU inside the rollout launch(es)
   solver = {'bound': 'issue', 'unit': 'lane-instructions/s', 'peak': lane_peak,
             'peak_source': 'blcd_measure_peaks in this run: fp32 FMA with every issue slot filled (x2 = %.1f TFLOP/s fp32)' % (2 * lane_peak / 1e12),

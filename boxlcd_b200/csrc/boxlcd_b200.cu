@@ -653,8 +653,8 @@ int launch_sized(BLCD_PENV* h, F f) {
 #if BLCD_PROFILE_ID == 0
     case 160: return f(std::integral_constant<int, 160>());
     case 192: return f(std::integral_constant<int, 192>());
-    case 224: return f(std::integral_constant<int, 224>());
 #endif
+    case 224: return f(std::integral_constant<int, 224>());
     case 256: return f(std::integral_constant<int, 256>());
 #if BLCD_PROFILE_ID == 0   // the large profile is only ever launched with 256 threads (or 128 as the shared-memory fallback)
     case 320: return f(std::integral_constant<int, 320>());
@@ -759,7 +759,7 @@ int BLCD_P(create)(const blcd_spec* spec_host, int64_t n_worlds, int device, uin
 #if BLCD_PROFILE_ID == 0
     const int sizes[] = {512, 448, 384, 320, 256, 224, 192, 160, 128, 64};
 #else
-    const int sizes[] = {256, 128};
+    const int sizes[] = {256, 224, 128};
 #endif
     bool known = false;
     for (int b : sizes) known |= (b == h->block);

@@ -299,6 +299,7 @@ def test_results_do_not_depend_on_the_block_size(name, monkeypatch):
     for a, b in zip(outs[0], o):
       assert (a == b).all()
   monkeypatch.delenv('BLCD_BLOCK')
+  monkeypatch.delenv('BLCD_PIPELINE', raising=False)    # the automatic path selection is what is checked below
   # wave-aware choices: 65 536 worlds are one wave of 448-thread blocks (also for articulated scenes, since round 2); 32 768
   # worlds (262 144 over 8 GPUs) one wave of 224-thread blocks; large batches go to the phase pipeline
   assert vec(make_env('Bounce2'), 65536).info()['block'] == 448 and vec(make_env('Urchin'), 65536).info()['block'] == 448
