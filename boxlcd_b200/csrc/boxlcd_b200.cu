@@ -746,6 +746,21 @@ int BLCD_P(create)(const blcd_spec* spec_host, int64_t n_worlds, int device, uin
       if (best == 0.0 || cost < best * 0.995) { best = cost; h->block = sizes[i]; }   // near-ties keep the smaller block
     }
   }
+#if BLCD_PROFILE_ID == 1
+  // large scenes: shared memory allows 256 or 224 threads; the smaller block wins when it fills the last wave (65 536 worlds:
+  // 1.73 waves of 256 but 1.98 of 224 -- CrabCube 1.27 -> 1.38 M env-steps/s, SpiderCube 2.86 -> 3.54 M)
+  if (n_worlds > (int64_t)sm_count * 128) {
+    const int sizes[] = {256, 224};
+    const double rel[] = {1.00, 0.90};
+    double best = 0.0;
+    for (int i = 0; i < 2; ++i) {
+      if (smem_bytes(h, sizes[i]) > (size_t)smem_max) continue;
+      const int64_t blocks = (n_worlds + sizes[i] - 1) / sizes[i], waves = (blocks + sm_count - 1) / sm_count;
+      const double cost = (double)waves * rel[i];
+      if (best == 0.0 || cost < best * 0.995) { best = cost; h->block = sizes[i]; }
+    }
+  }
+#endif
   if (const char* e = getenv("BLCD_BLOCK")) h->block = atoi(e);
   // Which device path steps this handle's worlds (both give the same results up to FMA-contraction-level round-off; each is
   // deterministic and independent of how the worlds are sharded):
