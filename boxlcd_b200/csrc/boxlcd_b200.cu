@@ -1047,7 +1047,22 @@ static int step_range(BLCD_PENV* h, const float* actions_dev, int n_steps, OutPt
     for (int i = 0; i < n_steps; ++i)
       if (pipeline_run(h, actions_dev, 0, 1, act_only, st, w_begin, w_end, slot, w_begin == 0 && w_end == h->n ? kHostStreams : 1)) return -1;
     o.actions = nullptr;
-    if (o.full_state || o.proprio || o.lcd_bits || o.lcd_bool || o.done) {
+    if (o.lcd_bits) {   // the frames by the body-major render kernel, straight from the state; k_observe then only packs full_state / proprio / done
+      if (!h->render_attr_set) {
+        CK(cudaFuncSetAttribute(k_render_poses, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kSceneBytes + sizeof(BodyPx) * kMaxBodies * kRenderMaxFrames + sizeof(RowInk) * kRenderThreads)));
+        CK(cudaFuncSetAttribute(k_render_bodies, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kSceneBytes + sizeof(RowInk) * kR2Frames * 256)));
+        h->render_attr_set = true;
+      }
+      const int64_t cnt_w = w_end - w_begin;
+      const int lw = row_words(h->scene.lcd_w);
+      k_render_bodies<<<(unsigned)((cnt_w + kR2Frames - 1) / kR2Frames), kR2Threads, (size_t)kSceneBytes + sizeof(RowInk) * kR2Frames * (size_t)h->scene.lcd_h, st>>>(
+          h->scene_dev, nullptr, nullptr, h->state, h->n, w_begin, cnt_w, h->scene.lcd_w, h->scene.lcd_h, o.lcd_bits + (size_t)w_begin * h->scene.lcd_h * lw,
+          0, h->scene.lcd_w, lw, 0, 1, 0);
+      CK(cudaGetLastError());
+      h->launches += 1;
+      o.lcd_bits = nullptr;
+    }
+    if (o.full_state || o.proprio || o.lcd_bool || o.done) {
       int rc = launch_sized(h, [&](auto B) {
         constexpr int BLOCK = decltype(B)::value;
         k_observe<BLOCK><<<(unsigned)((w_end - w_begin + BLOCK - 1) / BLOCK), BLOCK, smem_bytes(h, BLOCK), st>>>(h->scene_dev, h->state, h->n, o, w_begin, w_end);
