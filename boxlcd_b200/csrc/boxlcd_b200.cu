@@ -765,10 +765,11 @@ int BLCD_P(create)(const blcd_spec* spec_host, int64_t n_worlds, int device, uin
   // Which device path steps this handle's worlds (both give the same results up to FMA-contraction-level round-off; each is
   // deterministic and independent of how the worlds are sharded):
   //  * the phase pipeline (blcd_pipeline.cuh) once there are enough worlds to fill the GPU in every phase -- measured on a
-  //    B200 (Urchin): 19.2 M env-steps/s against 14.9 M at 131 072 worlds, 26.2 M against 16.4 M at 262 144, but 12.8 M against
-  //    14.7 M at 65 536 (its five kernels per sub-step each need their own wave of worlds);
+  //    B200 (Urchin, M env-steps/s, pipeline against fused): 28.7 / 16.4 at 262 144 worlds, 21.7 / 14.9 at 131 072, 17.3 / 15.2 at
+  //    98 304, 15.2 / 13.9 at 81 920, but 13.9 / 15.7 at 65 536 (its five kernels per sub-step each need their own wave of
+  //    worlds); joint-free scenes cross over later (Bounce2: 46.7 / 51.5 at 98 304, 87 / 52 at 262 144);
   //  * the fused one-thread-per-world kernel below that, and for single environments.
-  h->pipeline = n_worlds >= 98304;
+  h->pipeline = n_worlds >= (h->scene.nj > 0 ? 77824 : 106496);
   if (const char* e = getenv("BLCD_PIPELINE")) h->pipeline = atoi(e) != 0;
   {
 #if BLCD_PROFILE_ID == 0
@@ -1238,7 +1239,7 @@ static int host_chunks_default(BLCD_PENV* h) {
   }
   if (h->host_chunks_env > 0) return h->host_chunks_env;
   if (h->timing) return 1;
-  if (h->pipeline) return h->n >= 4 * 98304 ? 4 : (h->n >= 2 * 98304 ? 2 : 1);   // every range must still fill the GPU phase by phase
+  if (h->pipeline) return h->n >= 4 * 98304 ? 4 : (h->n >= 2 * 98304 ? 2 : 1);   // every range must still fill the GPU phase by phase (each is split further by pipeline_run only when it is the whole handle)
   // fused kernel: one block per SM, so a handle of at most one wave of blocks is stepped as ONE range (splitting it would round
   // every range up to whole blocks and spill into a second wave: 32 768 worlds in 8 ranges are 152 blocks of 224 on 148 SMs);
   // larger handles overlap the copies of one range with the kernel of the next
