@@ -1129,6 +1129,31 @@ struct Sim {
     q.ix = jr[h + J_IX]; q.iy = jr[h + J_IY]; q.iz = jr[h + J_IZ]; q.mi = jr[h + J_MI];
   }
 
+  // jv_load in two halves for the software-pipelined loop of solve_velocity: the loads of the NEXT joint's record are issued
+  // before the current joint is solved and only consumed (jv_derive) after it, so their latency hides behind that arithmetic
+  BLCD_HD void jv_fetch(JV& q, int j, float h_dt) const {
+    const DJoint& jd = sc.joint[j];
+    const int h = kHotJoint * j;
+    q.rowA = jd.a; q.rowB = jd.b;
+    uint32_t pk = jru(h + J_PK);
+    q.limitState = (int)(pk & 3u);
+    q.flags = (jd.enableMotor ? 1 : 0) | (jd.enableLimit ? 2 : 0) | (((pk >> 16) & 1u) ? 4 : 0);
+    q.rAx = jr[h + J_RAX]; q.rAy = jr[h + J_RAY]; q.rBx = jr[h + J_RBX]; q.rBy = jr[h + J_RBY];
+    q.exx = jr[h + J_EXX]; q.eyx = jr[h + J_EYX]; q.ezx = jr[h + J_EZX]; q.eyy = jr[h + J_EYY]; q.ezy = jr[h + J_EZY]; q.ezz = jr[h + J_EZZ];
+    q.mm = jr[h + J_MM]; q.maxImp = h_dt * jd.maxTorque; q.ms = jr[h + J_MS];
+    q.mA = hm(q.rowA); q.iA = hi(q.rowA); q.mB = hm(q.rowB); q.iB = hi(q.rowB);
+    q.ix = jr[h + J_IX]; q.iy = jr[h + J_IY]; q.iz = jr[h + J_IZ]; q.mi = jr[h + J_MI];
+  }
+  BLCD_HD void jv_derive(JV& q) const {
+    q.cx = q.eyy * q.ezz - q.ezy * q.ezy; q.cy = q.ezy * q.ezx - q.eyx * q.ezz; q.cz = q.eyx * q.ezy - q.eyy * q.ezx;  // cross(ey, ez)
+    float det = q.exx * q.cx + q.eyx * q.cy + q.ezx * q.cz;
+    if (det != 0.0f) det = 1.0f / det;
+    q.det3 = det;
+    float d2 = q.exx * q.eyy - q.eyx * q.eyx;
+    if (d2 != 0.0f) d2 = 1.0f / d2;
+    q.det2 = d2;
+  }
+
   BLCD_HD void jv_save(const JV& q, int j) {
     const int h = kHotJoint * j;
     jr[h + J_IX] = q.ix; jr[h + J_IY] = q.iy; jr[h + J_IZ] = q.iz; jr[h + J_MI] = q.mi;
@@ -1358,9 +1383,21 @@ struct Sim {
       if (njo > 1) jv_save(jb, jorder[1]);
       if (njo > 2) jv_save(jc, jorder[2]);
     } else {
+      // more joints than the register file holds (the crab-class robots have 16): their records stream from thread-local
+      // memory every sweep, the next one being fetched while the current one is solved
+      const int njo_ = njo, nc_ = nc;
       for (int it = 0; it < vi; ++it) {
-        for (int k = 0; k < njo; ++k) joint_solve_velocity(jorder[k], h_dt);
-        for (int k = 0; k < nc; ++k) contact_solve_velocity(k);
+        JV cur, nxt;
+        jv_fetch(cur, jorder[0], h_dt);
+        jv_derive(cur);
+        for (int k = 0; k < njo_; ++k) {
+          const int j = jorder[k];
+          if (k + 1 < njo_) jv_fetch(nxt, jorder[k + 1], h_dt);
+          jv_solve(cur);
+          jv_save(cur, j);
+          if (k + 1 < njo_) { jv_derive(nxt); cur = nxt; }
+        }
+        for (int k = 0; k < nc_; ++k) contact_solve_velocity(k);
       }
     }
     for (int k = 0; k < nc; ++k) contact_store_impulses(k);
