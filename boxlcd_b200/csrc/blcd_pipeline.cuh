@@ -35,16 +35,19 @@ BLCD_HD void pipe_pre(Sim<S>& sim, bool first, const float* action) {
   sim.store_after_setup();
 }
 
+// shared-memory words per thread of the velocity kernel's lean column
+BLCD_HD int pipe_vel_hot_words(const DScene& sc) { return 5 * (sc.nb + 1); }
+
 // phase 2.  No load(): everything comes from the scratch area; impulses go to the manifold slots / scratch.
 template <int S>
 BLCD_HD void pipe_vel(Sim<S>& sim) {
   sim.x_misc_in();
-  sim.x_rows_in(0, 8);
+  sim.oM = sim.oP;   // lean column: [v 3 x (nb+1)][invMass invI 2 x (nb+1)], positions stay in the scratch rows (pipe_vel_hot_words)
+  sim.x_rows_in_lean();
   sim.x_jr_in(0, kHotJoint);
   sim.x_cr_in();
   sim.solve_velocity(sim.scene().dt);
-  sim.solve_integrate(sim.scene().dt);
-  sim.x_rows_out(0, 6);
+  sim.solve_integrate_x(sim.scene().dt);
   sim.x_jr_out(J_IX, 4);
 }
 

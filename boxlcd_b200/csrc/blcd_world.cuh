@@ -237,6 +237,18 @@ struct Sim {
     hot[oM + 2 * nb] = 0.0f;
     hot[oM + 2 * nb + 1] = 0.0f;
   }
+  // lean variant for the velocity kernel, whose shared-memory column holds [v 3][invMass invI 2] per body and NO position
+  // rows (the caller has set oM = oP): 5 instead of 8 words per body and thread, so more blocks fit an SM
+  BLCD_HD void x_rows_in_lean() const {
+    const int nb = sc.nb;
+    for (int b = 0; b < nb; ++b) {
+      for (int k = 0; k < 3; ++k) hot[oV + 3 * b + k] = x.f(sc.x_rows + 8 * b + k);
+      for (int k = 0; k < 2; ++k) hot[oM + 2 * b + k] = x.f(sc.x_rows + 8 * b + 6 + k);
+    }
+    set_hv(nb, mk(0.0f, 0.0f), 0.0f);
+    hot[oM + 2 * nb] = 0.0f;
+    hot[oM + 2 * nb + 1] = 0.0f;
+  }
   BLCD_HD void x_misc_out() const {
     x.u(sc.x_misc) = (uint32_t)nc | ((uint32_t)njo << 8) | ((uint32_t)nIslands << 16);
     x.u(sc.x_misc + 1) = islDone;
@@ -1139,12 +1151,19 @@ struct Sim {
     q.limitState = (int)(pk & 3u);
     q.flags = (jd.enableMotor ? 1 : 0) | (jd.enableLimit ? 2 : 0) | (((pk >> 16) & 1u) ? 4 : 0);
     q.rAx = jr[h + J_RAX]; q.rAy = jr[h + J_RAY]; q.rBx = jr[h + J_RBX]; q.rBy = jr[h + J_RBY];
-    q.exx = jr[h + J_EXX]; q.eyx = jr[h + J_EYX]; q.ezx = jr[h + J_EZX]; q.eyy = jr[h + J_EYY]; q.ezy = jr[h + J_EZY]; q.ezz = jr[h + J_EZZ];
     q.mm = jr[h + J_MM]; q.maxImp = h_dt * jd.maxTorque; q.ms = jr[h + J_MS];
     q.mA = hm(q.rowA); q.iA = hi(q.rowA); q.mB = hm(q.rowB); q.iB = hi(q.rowB);
     q.ix = jr[h + J_IX]; q.iy = jr[h + J_IY]; q.iz = jr[h + J_IZ]; q.mi = jr[h + J_MI];
   }
   BLCD_HD void jv_derive(JV& q) const {
+    // the effective-mass matrix is recomputed from the anchors and masses (the expressions of joint_init_velocity) rather
+    // than streamed from the record: six words less traffic per joint and sweep
+    q.exx = q.mA + q.mB + q.rAy * q.rAy * q.iA + q.rBy * q.rBy * q.iB;
+    q.eyx = -q.rAy * q.rAx * q.iA - q.rBy * q.rBx * q.iB;
+    q.ezx = -q.rAy * q.iA - q.rBy * q.iB;
+    q.eyy = q.mA + q.mB + q.rAx * q.rAx * q.iA + q.rBx * q.rBx * q.iB;
+    q.ezy = q.rAx * q.iA + q.rBx * q.iB;
+    q.ezz = q.iA + q.iB;
     q.cx = q.eyy * q.ezz - q.ezy * q.ezy; q.cy = q.ezy * q.ezx - q.eyx * q.ezz; q.cz = q.eyx * q.ezy - q.eyy * q.ezx;  // cross(ey, ez)
     float det = q.exx * q.cx + q.eyx * q.cy + q.ezx * q.cz;
     if (det != 0.0f) det = 1.0f / det;
@@ -1418,6 +1437,28 @@ struct Sim {
       aa += h_dt * ww;
       set_hc(b, cc, aa);
       set_hv(b, vv, ww);
+    }
+  }
+
+  // the same with the positions read from and written to the scratch rows (lean velocity kernel), velocities spilled too
+  BLCD_HD void solve_integrate_x(float h_dt) {
+    const int nb = sc.nb;
+    for (int b = 0; b < nb; ++b) {
+      V2 vv = hv(b);
+      float ww = hw(b);
+      if (islandOf[b] >= 0) {
+        const int o = sc.x_rows + 8 * b;
+        V2 cc = mk(x.f(o + 3), x.f(o + 4));
+        float aa = x.f(o + 5);
+        V2 translation = h_dt * vv;
+        if (dot(translation, translation) > kMaxTranslationSq) { float ratio = kMaxTranslation / len(translation); vv *= ratio; }
+        float rotation = h_dt * ww;
+        if (rotation * rotation > kMaxRotationSq) { float ratio = kMaxRotation / absb(rotation); ww *= ratio; }
+        cc += h_dt * vv;
+        aa += h_dt * ww;
+        x.f(o + 3) = cc.x; x.f(o + 4) = cc.y; x.f(o + 5) = aa;
+      }
+      x.f(sc.x_rows + 8 * b) = vv.x; x.f(sc.x_rows + 8 * b + 1) = vv.y; x.f(sc.x_rows + 8 * b + 2) = ww;
     }
   }
 

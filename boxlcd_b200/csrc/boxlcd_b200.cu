@@ -642,6 +642,8 @@ struct BLCD_PENV {
 namespace {
 
 size_t smem_bytes(const BLCD_PENV* h, int block) { return (size_t)kSceneBytes + (size_t)h->scene.hot_words * block * sizeof(float); }
+// the velocity kernel keeps only velocity and mass rows on chip (blcd_pipeline.cuh: pipe_vel)
+size_t vel_smem_bytes(const BLCD_PENV* h) { return (size_t)kSceneBytes + (size_t)pipe_vel_hot_words(h->scene) * kPipeBlock * sizeof(float); }
 
 template <typename F>
 int launch_sized(BLCD_PENV* h, F f) {
@@ -942,7 +944,9 @@ static int pipeline_prepare(BLCD_PENV* h) {
   const size_t sb = smem_bytes(h, kPipeBlock);
   // shared memory for the blocks each kernel is compiled to keep resident; the rest of the SM's array is L1, which the
   // velocity / position kernels need for their thread-local contact records
-  if (set_smem_attr(k_pipe_pre, sb, kPreBlocks) || set_smem_attr(k_pipe_vel, sb, kVelBlocks) || set_smem_attr(k_pipe_pos, sb, kPosBlocks) ||
+  const size_t sbv = vel_smem_bytes(h);
+  const int vel_fit = (int)((227 * 1024) / (sbv + 1024));
+  if (set_smem_attr(k_pipe_pre, sb, kPreBlocks) || set_smem_attr(k_pipe_vel, sbv, vel_fit < kVelBlocks ? vel_fit : kVelBlocks) || set_smem_attr(k_pipe_pos, sb, kPosBlocks) ||
       set_smem_attr(k_pipe_post, sb, kPostBlocks) || set_smem_attr(k_pipe_toi, smem_bytes(h, kToiBlock), 16))
     return -1;
   for (int r = 0; r < kHostStreams; ++r) {
@@ -989,7 +993,7 @@ static void pipeline_substep(BLCD_PENV* h, const float* actions_dev, int mode, i
       k_pipe_pre<<<blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, h->seed, h->world_offset, actions_dev, mode, T, t, s == 0 ? 1 : 0, out,
                                                  w0, w1, cnt, h->pos_next + slot, bins, h->bin_list, pos_sort == 1);
       static const bool vel_sort = !(getenv("BLCD_VEL_SORT") && atoi(getenv("BLCD_VEL_SORT")) == 0);
-      k_pipe_vel<<<blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, w0, w1, bins, vel_sort ? h->bin_list : nullptr);
+      k_pipe_vel<<<blocks, kPipeBlock, vel_smem_bytes(h), st>>>(h->scene_dev, h->state, h->scratch, h->n, w0, w1, bins, vel_sort ? h->bin_list : nullptr);
       k_pipe_pos<<<pos_blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, w0, w1, h->pos_next + slot, pos_refill, bins, pos_sort ? h->bin_list : nullptr, pos_sort);
       k_pipe_post<<<blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, h->seed, h->world_offset, w0, w1, cnt, list, bins);
       static const bool dbg_toi = getenv("BLCD_DEBUG_TOI") != nullptr;   // diagnostic: share of worlds that reach the TOI kernel
