@@ -35,7 +35,7 @@ BLCD_HD void pipe_pre(Sim<S>& sim, bool first, const float* action) {
   sim.store_after_setup();
 }
 
-// shared-memory words per thread of the velocity kernel's lean column
+// shared-memory words per thread of the velocity and position kernels' lean columns
 BLCD_HD int pipe_vel_hot_words(const DScene& sc) { return 5 * (sc.nb + 1); }
 
 // phase 2.  No load(): everything comes from the scratch area; impulses go to the manifold slots / scratch.
@@ -56,6 +56,8 @@ template <int S>
 BLCD_HD void pipe_pos_begin(Sim<S>& sim) {
   sim.load_variant();
   sim.x_misc_in();
+  sim.oP = sim.oV; sim.oM = sim.oV + 3 * (sim.scene().nb + 1);   // (absolute: the persistent kernel comes through here once per world)
+  // lean column: [c a 3 x (nb+1)][invMass invI 2 x (nb+1)], no velocity rows in this kernel
   sim.x_rows_in(3, 5);
   sim.x_cr_pk_in();
   for (int k = 0; k < sim.nc; ++k) sim.pos_cache_manifold(k);   // manifold data is read once per world, not once per sweep

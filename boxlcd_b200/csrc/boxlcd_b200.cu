@@ -642,7 +642,7 @@ struct BLCD_PENV {
 namespace {
 
 size_t smem_bytes(const BLCD_PENV* h, int block) { return (size_t)kSceneBytes + (size_t)h->scene.hot_words * block * sizeof(float); }
-// the velocity kernel keeps only velocity and mass rows on chip (blcd_pipeline.cuh: pipe_vel)
+// the velocity kernel keeps only velocity and mass rows on chip, the position kernel only position and mass rows (blcd_pipeline.cuh)
 size_t vel_smem_bytes(const BLCD_PENV* h) { return (size_t)kSceneBytes + (size_t)pipe_vel_hot_words(h->scene) * kPipeBlock * sizeof(float); }
 
 template <typename F>
@@ -946,7 +946,8 @@ static int pipeline_prepare(BLCD_PENV* h) {
   // velocity / position kernels need for their thread-local contact records
   const size_t sbv = vel_smem_bytes(h);
   const int vel_fit = (int)((227 * 1024) / (sbv + 1024));
-  if (set_smem_attr(k_pipe_pre, sb, kPreBlocks) || set_smem_attr(k_pipe_vel, sbv, vel_fit < kVelBlocks ? vel_fit : kVelBlocks) || set_smem_attr(k_pipe_pos, sb, kPosBlocks) ||
+  if (set_smem_attr(k_pipe_pre, sb, kPreBlocks) || set_smem_attr(k_pipe_vel, sbv, vel_fit < kVelBlocks ? vel_fit : kVelBlocks) ||
+      set_smem_attr(k_pipe_pos, sbv, vel_fit < kPosBlocks ? vel_fit : kPosBlocks) ||
       set_smem_attr(k_pipe_post, sb, kPostBlocks) || set_smem_attr(k_pipe_toi, smem_bytes(h, kToiBlock), 16))
     return -1;
   for (int r = 0; r < kHostStreams; ++r) {
@@ -969,7 +970,9 @@ static void pipeline_substep(BLCD_PENV* h, const float* actions_dev, int mode, i
   uint32_t* bins = h->bin_count + slot * kAllBins;
   // the position kernel is persistent: as many blocks as can be resident, never more than there are worlds for
   static const int pos_resident = getenv("BLCD_POS_BLOCKS") ? atoi(getenv("BLCD_POS_BLOCKS")) : kPosBlocks;
-  unsigned pos_blocks = (unsigned)(h->sm_count * (pos_resident < 1 ? 1 : (pos_resident > kPosBlocks ? kPosBlocks : pos_resident)));
+  const int pos_fit = (int)((227 * 1024) / (vel_smem_bytes(h) + 1024));
+  const int pos_cap = pos_fit < kPosBlocks ? (pos_fit < 1 ? 1 : pos_fit) : kPosBlocks;
+  unsigned pos_blocks = (unsigned)(h->sm_count * (pos_resident < 1 ? 1 : (pos_resident > pos_cap ? pos_cap : pos_resident)));
   if (pos_blocks > blocks) pos_blocks = blocks;
   static const int pos_sort = getenv("BLCD_POS_SORT") ? atoi(getenv("BLCD_POS_SORT")) : 2;   // 0 world order, 1 by previous sweep count, 2 by contact count
   static const int pos_refill = getenv("BLCD_POS_REFILL") ? atoi(getenv("BLCD_POS_REFILL")) : 16;
@@ -994,7 +997,7 @@ static void pipeline_substep(BLCD_PENV* h, const float* actions_dev, int mode, i
                                                  w0, w1, cnt, h->pos_next + slot, bins, h->bin_list, pos_sort == 1);
       static const bool vel_sort = !(getenv("BLCD_VEL_SORT") && atoi(getenv("BLCD_VEL_SORT")) == 0);
       k_pipe_vel<<<blocks, kPipeBlock, vel_smem_bytes(h), st>>>(h->scene_dev, h->state, h->scratch, h->n, w0, w1, bins, vel_sort ? h->bin_list : nullptr);
-      k_pipe_pos<<<pos_blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, w0, w1, h->pos_next + slot, pos_refill, bins, pos_sort ? h->bin_list : nullptr, pos_sort);
+      k_pipe_pos<<<pos_blocks, kPipeBlock, vel_smem_bytes(h), st>>>(h->scene_dev, h->state, h->scratch, h->n, w0, w1, h->pos_next + slot, pos_refill, bins, pos_sort ? h->bin_list : nullptr, pos_sort);
       k_pipe_post<<<blocks, kPipeBlock, sb, st>>>(h->scene_dev, h->state, h->scratch, h->n, h->seed, h->world_offset, w0, w1, cnt, list, bins);
       static const bool dbg_toi = getenv("BLCD_DEBUG_TOI") != nullptr;   // diagnostic: share of worlds that reach the TOI kernel
       if (dbg_toi) {

@@ -124,7 +124,9 @@ void pipeline_env_step(HostSim* h, int64_t w, const float* act) {
   for (int s = 0; s < h->scene.nsub; ++s) {
     { Phase p(h, w, true); pipe_pre(*p.sim, s == 0, act); }
     { Phase p(h, w, false); pipe_vel(*p.sim); }
-    { Phase p(h, w, false); pipe_pos(*p.sim); }
+    // the device kernel is persistent: one Sim object comes through pipe_pos_begin once per world it fetches, so the begin
+    // must not depend on what an earlier begin left in the object -- entered twice here to catch that
+    { Phase p(h, w, false); pipe_pos_begin(*p.sim); pipe_pos(*p.sim); }
     bool need;
     { Phase p(h, w, true); need = pipe_post(*p.sim); }
     if (need) { Phase p(h, w, true); pipe_toi(*p.sim); }
