@@ -771,7 +771,9 @@ int BLCD_P(create)(const blcd_spec* spec_host, int64_t n_worlds, int device, uin
   //    98 304, 15.2 / 13.9 at 81 920, but 13.9 / 15.7 at 65 536 (its five kernels per sub-step each need their own wave of
   //    worlds); joint-free scenes cross over later (Bounce2: 46.7 / 51.5 at 98 304, 87 / 52 at 262 144);
   //  * the fused one-thread-per-world kernel below that, and for single environments.
-  h->pipeline = n_worlds >= (h->scene.nj > 0 ? 77824 : 106496);
+  //    the crab robots (16 joints) already at 65 536 (CrabCube 2.03 / 1.91; SpiderCube, 8 joints, still 4.44 / 4.88 there and
+  //    5.77 / 4.91 at 98 304);
+  h->pipeline = n_worlds >= (h->scene.nj > 12 ? 65536 : (h->scene.nj > 0 ? 77824 : 106496));
   if (const char* e = getenv("BLCD_PIPELINE")) h->pipeline = atoi(e) != 0;
   {
 #if BLCD_PROFILE_ID == 0
