@@ -6,6 +6,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 
 #ifdef __CUDACC__
 #define BLCD_HD __host__ __device__ __forceinline__

@@ -46,7 +46,7 @@ BLCD_HD void pipe_vel(Sim<S>& sim) {
   sim.x_rows_in_lean();
   sim.x_jr_in(0, kHotJoint);
   sim.x_cr_in();
-  sim.solve_velocity(sim.scene().dt);
+  sim.template solve_velocity<true>(sim.scene().dt);
   sim.solve_integrate_x(sim.scene().dt);
   sim.x_jr_out(J_IX, 4);
 }

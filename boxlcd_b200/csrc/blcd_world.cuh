@@ -738,31 +738,57 @@ struct Sim {
   }
 
   // returns true if any impulse applied by this sweep was non-zero
-  BLCD_HD bool contact_solve_velocity(int k) {
-    const int h = kHotCon * k;
-    uint32_t pk = cru(h + C_PK);
+  BLCD_HD bool contact_solve_velocity(int k) { return contact_solve_velocity_rec(cr + kHotCon * k); }
+
+  // the solve on a record given by address: r points into cr[] (above) or at a register copy of one record (the streamed
+  // loop of solve_velocity); every index below is a compile-time constant once the two-point loops are unrolled
+  BLCD_HD static uint32_t rec_bits(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+  }
+  // register copy of the k-th record (both points' words: which are live is only known from the record itself) and the
+  // write-back of the four impulse words a solve may change
+  BLCD_HD void rec_fetch(float (&r)[kHotCon], int k) const {
+    const float* p = cr + kHotCon * k;
+#pragma unroll
+    for (int i = 0; i < kHotCon; ++i) r[i] = p[i];
+  }
+  BLCD_HD void rec_save(const float (&r)[kHotCon], int k) {
+    float* p = cr + kHotCon * k;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      p[C_PT + kHotConPt * j + P_NI] = r[C_PT + kHotConPt * j + P_NI];
+      p[C_PT + kHotConPt * j + P_TI] = r[C_PT + kHotConPt * j + P_TI];
+    }
+  }
+  BLCD_HD bool contact_solve_velocity_rec(float* r) {
+    uint32_t pk = rec_bits(r[C_PK]);
     int rA_ = pk & 31u, rB_ = (pk >> 5) & 31u, count = (pk >> 10) & 3u;
-    if (rA_ == nbS) return contact_solve_velocity_wall(h, rB_, count);
+    if (rA_ == nbS) return contact_solve_velocity_wall(r, rB_, count);
     float mA = hm(rA_), iA = hi(rA_), mB = hm(rB_), iB = hi(rB_);
     V2 vA = hv(rA_), vB = hv(rB_);
     float wA = hw(rA_), wB = hw(rB_);
-    V2 normal = mk(cr[h + C_NX], cr[h + C_NY]);
+    V2 normal = mk(r[C_NX], r[C_NY]);
     V2 tangent = cross(normal, 1.0f);
-    float friction = cr[h + C_FR];
+    float friction = r[C_FR];
     bool changed = false;
+#pragma unroll
     for (int j = 0; j < 2; ++j) {
       if (j < count) {
-        int q = h + C_PT + kHotConPt * j;
-        V2 rA = mk(cr[q + P_RAX], cr[q + P_RAY]), rB = mk(cr[q + P_RBX], cr[q + P_RBY]);
+        const int q = C_PT + kHotConPt * j;
+        V2 rA = mk(r[q + P_RAX], r[q + P_RAY]), rB = mk(r[q + P_RBX], r[q + P_RBY]);
         V2 dv = vB + cross(wB, rB) - vA - cross(wA, rA);
         float vt = dot(dv, tangent) - 0.0f;
-        float lambda = cr[q + P_TM] * (-vt);
-        float maxFriction = friction * cr[q + P_NI];
-        float oldImpulse = cr[q + P_TI];
+        float lambda = r[q + P_TM] * (-vt);
+        float maxFriction = friction * r[q + P_NI];
+        float oldImpulse = r[q + P_TI];
         float newImpulse = clampb(oldImpulse + lambda, -maxFriction, maxFriction);
         lambda = newImpulse - oldImpulse;
         changed |= (lambda != 0.0f);
-        cr[q + P_TI] = newImpulse;
+        r[q + P_TI] = newImpulse;
         V2 P = lambda * tangent;
         vA -= mA * P;
         wA -= iA * cross(rA, P);
@@ -771,32 +797,32 @@ struct Sim {
       }
     }
     if (count == 1) {
-      int q = h + C_PT;
-      V2 rA = mk(cr[q + P_RAX], cr[q + P_RAY]), rB = mk(cr[q + P_RBX], cr[q + P_RBY]);
+      const int q = C_PT;
+      V2 rA = mk(r[q + P_RAX], r[q + P_RAY]), rB = mk(r[q + P_RBX], r[q + P_RBY]);
       V2 dv = vB + cross(wB, rB) - vA - cross(wA, rA);
       float vn = dot(dv, normal);
-      float lambda = -cr[q + P_NM] * (vn - cr[q + P_BIAS]);
-      float oldImpulse = cr[q + P_NI];
+      float lambda = -r[q + P_NM] * (vn - r[q + P_BIAS]);
+      float oldImpulse = r[q + P_NI];
       float newImpulse = fmaxb(oldImpulse + lambda, 0.0f);
       lambda = newImpulse - oldImpulse;
       changed |= (lambda != 0.0f);
-      cr[q + P_NI] = newImpulse;
+      r[q + P_NI] = newImpulse;
       V2 P = lambda * normal;
       vA -= mA * P;
       wA -= iA * cross(rA, P);
       vB += mB * P;
       wB += iB * cross(rB, P);
     } else if (count == 2) {
-      int q1 = h + C_PT, q2 = h + C_PT + kHotConPt;
-      V2 r1A = mk(cr[q1 + P_RAX], cr[q1 + P_RAY]), r1B = mk(cr[q1 + P_RBX], cr[q1 + P_RBY]);
-      V2 r2A = mk(cr[q2 + P_RAX], cr[q2 + P_RAY]), r2B = mk(cr[q2 + P_RBX], cr[q2 + P_RBY]);
-      V2 aa = mk(cr[q1 + P_NI], cr[q2 + P_NI]);
+      const int q1 = C_PT, q2 = C_PT + kHotConPt;
+      V2 r1A = mk(r[q1 + P_RAX], r[q1 + P_RAY]), r1B = mk(r[q1 + P_RBX], r[q1 + P_RBY]);
+      V2 r2A = mk(r[q2 + P_RAX], r[q2 + P_RAY]), r2B = mk(r[q2 + P_RBX], r[q2 + P_RBY]);
+      V2 aa = mk(r[q1 + P_NI], r[q2 + P_NI]);
       V2 dv1 = vB + cross(wB, r1B) - vA - cross(wA, r1A);
       V2 dv2 = vB + cross(wB, r2B) - vA - cross(wA, r2A);
       float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
-      V2 b = mk(vn1 - cr[q1 + P_BIAS], vn2 - cr[q2 + P_BIAS]);
+      V2 b = mk(vn1 - r[q1 + P_BIAS], vn2 - r[q2 + P_BIAS]);
       V2 x;
-      bool found = block_solve(h, q1, q2, aa, b, x);
+      bool found = block_solve(r, q1, q2, aa, b, x);
       if (found) {
         V2 d = x - aa;
         changed |= (d.x != 0.0f) | (d.y != 0.0f);
@@ -805,8 +831,8 @@ struct Sim {
         wA -= iA * (cross(r1A, P1) + cross(r2A, P2));
         vB += mB * (P1 + P2);
         wB += iB * (cross(r1B, P1) + cross(r2B, P2));
-        cr[q1 + P_NI] = x.x;
-        cr[q2 + P_NI] = x.y;
+        r[q1 + P_NI] = x.x;
+        r[q2 + P_NI] = x.y;
       }
     }
     set_hv(rA_, vA, wA);
@@ -815,16 +841,16 @@ struct Sim {
   }
 
   // b2ContactSolver's 2-point block LCP (cases 1-4); b is vn - bias, already reduced by K a inside
-  BLCD_HD bool block_solve(int h, int q1, int q2, V2 aa, V2 b, V2& x) const {
-    float k11 = cr[h + C_K11], k12 = cr[h + C_K12], k22 = cr[h + C_K22];
+  BLCD_HD bool block_solve(const float* r, int q1, int q2, V2 aa, V2 b, V2& x) const {
+    float k11 = r[C_K11], k12 = r[C_K12], k22 = r[C_K22];
     b -= mk(k11 * aa.x + k12 * aa.y, k12 * aa.x + k22 * aa.y);
-    float n11 = cr[h + C_N11], n12 = cr[h + C_N12], n22 = cr[h + C_N22];
+    float n11 = r[C_N11], n12 = r[C_N12], n22 = r[C_N22];
     x = -mk(n11 * b.x + n12 * b.y, n12 * b.x + n22 * b.y);
     if (x.x >= 0.0f && x.y >= 0.0f) return true;
-    x.x = -cr[q1 + P_NM] * b.x; x.y = 0.0f;
+    x.x = -r[q1 + P_NM] * b.x; x.y = 0.0f;
     float vn2 = k12 * x.x + b.y;
     if (x.x >= 0.0f && vn2 >= 0.0f) return true;
-    x.x = 0.0f; x.y = -cr[q2 + P_NM] * b.y;
+    x.x = 0.0f; x.y = -r[q2 + P_NM] * b.y;
     float vn1 = k12 * x.y + b.x;
     if (x.y >= 0.0f && vn1 >= 0.0f) return true;
     x.x = 0.0f; x.y = 0.0f;
@@ -833,64 +859,65 @@ struct Sim {
 
   // contact against a wall: body A is the static row, whose velocity and inverse masses are exactly zero, so every
   // A-side term of b2ContactSolver::SolveVelocityConstraints is an exact +-0 and is skipped
-  BLCD_HD bool contact_solve_velocity_wall(int h, int rB_, int count) {
+  BLCD_HD bool contact_solve_velocity_wall(float* r, int rB_, int count) {
     float mB = hm(rB_), iB = hi(rB_);
     V2 vB = hv(rB_);
     float wB = hw(rB_);
-    V2 normal = mk(cr[h + C_NX], cr[h + C_NY]);
+    V2 normal = mk(r[C_NX], r[C_NY]);
     V2 tangent = cross(normal, 1.0f);
-    float friction = cr[h + C_FR];
+    float friction = r[C_FR];
     bool changed = false;
+#pragma unroll
     for (int j = 0; j < 2; ++j) {
       if (j < count) {
-        int q = h + C_PT + kHotConPt * j;
-        V2 rB = mk(cr[q + P_RBX], cr[q + P_RBY]);
+        const int q = C_PT + kHotConPt * j;
+        V2 rB = mk(r[q + P_RBX], r[q + P_RBY]);
         V2 dv = vB + cross(wB, rB);
         float vt = dot(dv, tangent) - 0.0f;
-        float lambda = cr[q + P_TM] * (-vt);
-        float maxFriction = friction * cr[q + P_NI];
-        float oldImpulse = cr[q + P_TI];
+        float lambda = r[q + P_TM] * (-vt);
+        float maxFriction = friction * r[q + P_NI];
+        float oldImpulse = r[q + P_TI];
         float newImpulse = clampb(oldImpulse + lambda, -maxFriction, maxFriction);
         lambda = newImpulse - oldImpulse;
         changed |= (lambda != 0.0f);
-        cr[q + P_TI] = newImpulse;
+        r[q + P_TI] = newImpulse;
         V2 P = lambda * tangent;
         vB += mB * P;
         wB += iB * cross(rB, P);
       }
     }
     if (count == 1) {
-      int q = h + C_PT;
-      V2 rB = mk(cr[q + P_RBX], cr[q + P_RBY]);
+      const int q = C_PT;
+      V2 rB = mk(r[q + P_RBX], r[q + P_RBY]);
       V2 dv = vB + cross(wB, rB);
       float vn = dot(dv, normal);
-      float lambda = -cr[q + P_NM] * (vn - cr[q + P_BIAS]);
-      float oldImpulse = cr[q + P_NI];
+      float lambda = -r[q + P_NM] * (vn - r[q + P_BIAS]);
+      float oldImpulse = r[q + P_NI];
       float newImpulse = fmaxb(oldImpulse + lambda, 0.0f);
       lambda = newImpulse - oldImpulse;
       changed |= (lambda != 0.0f);
-      cr[q + P_NI] = newImpulse;
+      r[q + P_NI] = newImpulse;
       V2 P = lambda * normal;
       vB += mB * P;
       wB += iB * cross(rB, P);
     } else if (count == 2) {
-      int q1 = h + C_PT, q2 = h + C_PT + kHotConPt;
-      V2 r1B = mk(cr[q1 + P_RBX], cr[q1 + P_RBY]), r2B = mk(cr[q2 + P_RBX], cr[q2 + P_RBY]);
-      V2 aa = mk(cr[q1 + P_NI], cr[q2 + P_NI]);
+      const int q1 = C_PT, q2 = C_PT + kHotConPt;
+      V2 r1B = mk(r[q1 + P_RBX], r[q1 + P_RBY]), r2B = mk(r[q2 + P_RBX], r[q2 + P_RBY]);
+      V2 aa = mk(r[q1 + P_NI], r[q2 + P_NI]);
       V2 dv1 = vB + cross(wB, r1B);
       V2 dv2 = vB + cross(wB, r2B);
       float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
-      V2 b = mk(vn1 - cr[q1 + P_BIAS], vn2 - cr[q2 + P_BIAS]);
+      V2 b = mk(vn1 - r[q1 + P_BIAS], vn2 - r[q2 + P_BIAS]);
       V2 x;
-      bool found = block_solve(h, q1, q2, aa, b, x);
+      bool found = block_solve(r, q1, q2, aa, b, x);
       if (found) {
         V2 d = x - aa;
         changed |= (d.x != 0.0f) | (d.y != 0.0f);
         V2 P1 = d.x * normal, P2 = d.y * normal;
         vB += mB * (P1 + P2);
         wB += iB * (cross(r1B, P1) + cross(r2B, P2));
-        cr[q1 + P_NI] = x.x;
-        cr[q2 + P_NI] = x.y;
+        r[q1 + P_NI] = x.x;
+        r[q2 + P_NI] = x.y;
       }
     }
     set_hv(rB_, vB, wB);
@@ -1379,6 +1406,9 @@ struct Sim {
   }
 
   // b2Island::Solve's velocity iterations + b2ContactSolver::StoreImpulses
+  // STREAM_CONTACTS: the pipeline's velocity kernel (128 registers, nothing else live) also streams the contact records of
+  // many-joint scenes through registers; the fused kernels do not (no registers to spare: SpiderCube -6 % when they did)
+  template <bool STREAM_CONTACTS = false>
   BLCD_HD void solve_velocity(float h_dt) {
     const int vi = sc.vel_iters;
     if (njo <= 3) {
@@ -1405,6 +1435,38 @@ struct Sim {
       // more joints than the register file holds (the crab-class robots have 16): their records stream from thread-local
       // memory every sweep, the next one being fetched while the current one is solved
       const int njo_ = njo, nc_ = nc;
+#if BLCD_PROFILE_ID == 1
+      // The contact records stream the same way, through two register copies (ra: being solved, rb: arriving).  Large-scene
+      // build only: in the small build (4-7 joints: none of the reference's robots) the two copies land on the stack of the
+      // fused kernel and cost the THREE-joint robots 12 % (Urchin, 32 768 worlds: 14.5 -> 12.7 M env-steps/s, measured).
+      if (STREAM_CONTACTS) {
+        JV cur, nxt;
+        float ra[kHotCon], rb[kHotCon];
+        jv_fetch(cur, jorder[0], h_dt);
+        for (int it = 0; it < vi; ++it) {
+          jv_derive(cur);
+          for (int k = 0; k < njo_; ++k) {
+            const int j = jorder[k];
+            if (k + 1 < njo_) jv_fetch(nxt, jorder[k + 1], h_dt);
+            else if (nc_ > 0) rec_fetch(ra, 0);
+            jv_solve(cur);
+            jv_save(cur, j);
+            if (k + 1 < njo_) { jv_derive(nxt); cur = nxt; }
+          }
+          for (int k = 0; k < nc_; ++k) {
+            if (k + 1 < nc_) rec_fetch(rb, k + 1);
+            else if (it + 1 < vi) jv_fetch(cur, jorder[0], h_dt);
+            contact_solve_velocity_rec(ra);
+            rec_save(ra, k);
+            if (k + 1 < nc_) {
+#pragma unroll
+              for (int i = 0; i < kHotCon; ++i) ra[i] = rb[i];
+            }
+          }
+          if (nc_ == 0 && it + 1 < vi) jv_fetch(cur, jorder[0], h_dt);
+        }
+      } else
+#endif
       for (int it = 0; it < vi; ++it) {
         JV cur, nxt;
         jv_fetch(cur, jorder[0], h_dt);
