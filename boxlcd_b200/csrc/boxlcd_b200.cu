@@ -771,9 +771,9 @@ int BLCD_P(create)(const blcd_spec* spec_host, int64_t n_worlds, int device, uin
   //    98 304, 15.2 / 13.9 at 81 920, but 13.9 / 15.7 at 65 536 (its five kernels per sub-step each need their own wave of
   //    worlds); joint-free scenes cross over later (Bounce2: 46.7 / 51.5 at 98 304, 87 / 52 at 262 144);
   //  * the fused one-thread-per-world kernel below that, and for single environments.
-  //    the crab robots (16 joints) already at 65 536 (CrabCube 2.03 / 1.91; SpiderCube, 8 joints, still 4.44 / 4.88 there and
-  //    5.77 / 4.91 at 98 304);
-  h->pipeline = n_worlds >= (h->scene.nj > 12 ? 65536 : (h->scene.nj > 0 ? 77824 : 106496));
+  //    the crab-class scenes of the large build already at 65 536 (CrabCube 2.38 / 1.91, SpiderCube 4.95 / 4.79; eight
+  //    world ranges, pipeline_run);
+  h->pipeline = n_worlds >= (BLCD_PROFILE_ID == 1 ? 65536 : (h->scene.nj > 0 ? 77824 : 106496));
   if (const char* e = getenv("BLCD_PIPELINE")) h->pipeline = atoi(e) != 0;
   {
 #if BLCD_PROFILE_ID == 0
@@ -1023,10 +1023,12 @@ static int pipeline_run(BLCD_PENV* h, const float* actions_dev, int mode, int T,
   if (w1 <= w0) return 0;
   // measured (Urchin): 131 072 worlds 19.6 M env-steps/s as one range, 20.9 M as two, 21.7 M as four; 262 144 worlds 25.6 / 26.2 / 25.1 M
   static const int want = getenv("BLCD_PIPE_RANGES") ? atoi(getenv("BLCD_PIPE_RANGES")) : 0;
-  int R = want > 0 ? want : ((w1 - w0) < 196608 ? 4 : 2);
+  // crab-class scenes (large build; two or three resident blocks per SM in every kernel): CrabCube 65 536 worlds 2.11 / 2.21 / 2.25 /
+  // 2.36 M as 1 / 2 / 4 / 8 ranges, 131 072 worlds 2.53 / 2.80 / 2.88 / 2.89 M; SpiderCube indifferent from 4 on
+  int R = want > 0 ? want : (BLCD_PROFILE_ID == 1 ? 8 : ((w1 - w0) < 196608 ? 4 : 2));
   R = R > max_ranges ? max_ranges : R;
   const int64_t gran = 4 * kPipeBlock;
-  static const int64_t min_range = getenv("BLCD_PIPE_MIN_RANGE") ? atoll(getenv("BLCD_PIPE_MIN_RANGE")) : 24576;
+  static const int64_t min_range = getenv("BLCD_PIPE_MIN_RANGE") ? atoll(getenv("BLCD_PIPE_MIN_RANGE")) : (BLCD_PROFILE_ID == 1 ? 8192 : 24576);
   while (R > 1 && (w1 - w0) / R < min_range) --R;    // small ranges cannot fill the GPU: the interleaving only pays with enough worlds each
   if (R == 1) {
     for (int t = 0; t < T; ++t)

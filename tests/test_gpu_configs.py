@@ -305,7 +305,8 @@ def test_results_do_not_depend_on_the_block_size(name, monkeypatch):
   assert vec(make_env('Bounce2'), 65536).info()['block'] == 448 and vec(make_env('Urchin'), 65536).info()['block'] == 448
   assert vec(make_env('Urchin'), 32768).info()['block'] == 224 and vec(make_env('Urchin'), 32768).info()['pipeline'] == 0
   assert vec(make_env('Urchin'), 131072).info()['pipeline'] == 1
-  assert vec(make_env('CrabCube'), 65536).info()['pipeline'] == 1 and vec(make_env('SpiderCube'), 65536).info()['pipeline'] == 0
+  assert vec(make_env('CrabCube'), 65536).info()['pipeline'] == 1 and vec(make_env('SpiderCube'), 65536).info()['pipeline'] == 1
+  assert vec(make_env('SpiderCube'), 32768).info()['pipeline'] == 0
 
 
 def test_rekeyed_handle_equals_a_fresh_one_and_splits_differ(tmp_path):
